@@ -1,0 +1,178 @@
+/*
+ * wtracker_b200 — C ABI of the B200-native detect+predict hot path.
+ *
+ * The reference (giladfrid009/WTracker) has no FFI of its own: its plugin boundary is the Python
+ * ABC `SimController` (wtracker/sim/simulator.py:197-293) and the arithmetic below runs inside
+ * ultralytics / torch / cv2 / numpy on its behalf.  Each entry point cites the reference code whose
+ * arithmetic it replaces.  Conventions:
+ *
+ *   - every pointer is a raw DEVICE pointer unless named `h_*`; PyTorch (or any caller) owns all
+ *     memory including the engine workspace; no entry point allocates, frees or synchronises,
+ *     except wt_engine_create/destroy (host-side bookkeeping only) and wt_selftest_* (test only);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 = ok, non-zero = error; wt_last_error() gives a thread-local message;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute call fails.
+ */
+#ifndef WTRACKER_B200_H
+#define WTRACKER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------ */
+/* errors / info                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+const char* wt_last_error(void);
+int wt_abi_version(void);
+/* Number of kernel launches issued by this library since load (all threads). bench.py's
+ * `gpu_launches` is the difference of two readings. */
+uint64_t wt_launch_count(void);
+/* Fills sm count / compute capability of the current device. */
+int wt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K1-K4  camera-view crop + letterbox resize                                                 */
+/*   replaces ViewController.read/_custom_view (wtracker/sim/view_controller.py:45-61,158-172) */
+/*   cv.cvtColor GRAY2BGR (wtracker/sim/sim_controllers/yolo_controller.py:68-69) and the      */
+/*   ultralytics LetterBox + preprocess that predict() runs (yolo_controller.py:72-78).        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct wt_letterbox {
+    int32_t src_w, src_h;     /* camera view size (w,h) in px (crop taken from the frame)      */
+    int32_t dst_w, dst_h;     /* letterboxed network input size                                */
+    int32_t new_w, new_h;     /* resized (unpadded) size; new == src -> no resampling          */
+    int32_t pad_left, pad_top;/* letterbox padding (value 114)                                 */
+    /* cv2 INTER_LINEAR u8 fixed-point tables, device pointers (ignored when new == src):      */
+    const int32_t* xofs;      /* [new_w]   left source column                                  */
+    const int16_t* xcoef;     /* [new_w*2] 11-bit weights                                      */
+    const int32_t* yofs;      /* [new_h]   top source row                                      */
+    const int16_t* ycoef;     /* [new_h*2]                                                     */
+} wt_letterbox;
+
+/* frames : u8 [n_frames][frame_h][frame_w] grayscale, resident in HBM
+ * frame_idx[i], crop_x[i], crop_y[i] : per output image i, source frame and the crop origin in
+ *          FRAME coordinates (= position - size//2, may be negative or run past the frame:
+ *          border pixels replicate, as cv.copyMakeBorder(BORDER_REPLICATE) + slicing does)
+ * out_u8 : u8 [n][dst_h][dst_w] letterboxed grey image (the product path; conv0 folds /255 and
+ *          the 3 identical channels), or NULL
+ * out_f32: f32 [n][3][dst_h][dst_w] in [0,1] — the tensor ultralytics would feed the net, or NULL */
+int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, int frame_w,
+                  const int32_t* frame_idx, const int32_t* crop_x, const int32_t* crop_y, int n,
+                  const wt_letterbox* lb, uint8_t* out_u8, float* out_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K5  YOLOv8s backbone/neck/head as a program of fused ops over NHWC bf16 buffers            */
+/*   replaces ultralytics AutoBackend.forward (called from yolo_controller.py:72-78)           */
+/* ------------------------------------------------------------------------------------------ */
+enum { WT_OP_CONV0 = 0, WT_OP_CONV = 1, WT_OP_SPPF_POOL = 2, WT_OP_UPSAMPLE2X = 3 };
+enum { WT_ACT_NONE = 0, WT_ACT_SILU = 1 };
+enum { WT_DT_BF16 = 0, WT_DT_F32 = 1, WT_DT_U8 = 2 };
+
+typedef struct wt_buf {          /* one NHWC activation buffer (batch = engine batch)          */
+    int32_t h, w, c;             /* c = total channels (concat destinations hold all parts)    */
+    int32_t dtype;               /* WT_DT_*                                                    */
+} wt_buf;
+
+typedef struct wt_op {
+    int32_t kind;                /* WT_OP_*                                                    */
+    int32_t src, src_coff;       /* source buffer id, first channel                            */
+    int32_t dst, dst_coff;       /* destination buffer id, first channel                       */
+    int32_t res, res_coff;       /* residual buffer id (-1 = none), first channel              */
+    int32_t cin, cout;           /* conv channels (UPSAMPLE/POOL: cin = channels moved)        */
+    int32_t k, stride;           /* kernel size (1|3), stride (1|2); pad = k/2                 */
+    int32_t act;                 /* WT_ACT_*                                                   */
+    int64_t w_off, b_off;        /* byte offsets into the weight blob:                         */
+                                 /*   CONV : bf16 [cout][k][k][cin], f32 bias[cout]            */
+                                 /*   CONV0: f32 [cout][3][3] (grey-folded, /255 folded), f32 bias */
+} wt_op;
+
+typedef struct wt_engine wt_engine;
+
+/* bytes of workspace needed for `batch` images with these buffers */
+int64_t wt_engine_workspace_bytes(const wt_buf* bufs, int n_bufs, int batch);
+/* conv_impl: 0 = tcgen05 implicit GEMM (product), 1 = scalar validation kernel (tests only).
+ * weights/workspace are device pointers that must outlive the engine. */
+int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops, int n_ops, int batch,
+                     const void* weights, int64_t weight_bytes, void* workspace, int64_t workspace_bytes,
+                     int conv_impl, wt_engine** out);
+void wt_engine_destroy(wt_engine* e);
+/* device address of buffer `id` ([batch][h][w][c]) */
+void* wt_engine_buffer(wt_engine* e, int id);
+/* run ops [first, last) for the first n (<= batch) images; buffer 0 must hold the input */
+int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K6-K8  DFL decode + confidence filter + NMS + scale_boxes                                  */
+/*   replaces ultralytics Detect._inference / non_max_suppression / scale_boxes and the        */
+/*   first-box / NaN-row logic of YoloController.predict (yolo_controller.py:80-90)            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct wt_head_level {
+    const void* box;        /* [n][h*w][64] box-branch logits (4 sides x 16 DFL bins), box_dtype */
+    const void* cls_feat;   /* [n][h*w][cls_c] bf16 features feeding the final 1x1 cls conv, or  */
+    const float* cls_logit; /* [n][h*w] f32 ready-made class logits (oracle-fed tests); one of   */
+                            /* cls_feat / cls_logit is non-NULL                                  */
+    int32_t h, w, stride;   /* grid and stride (8/16/32)                                         */
+    int32_t box_dtype;      /* WT_DT_BF16 | WT_DT_F32                                            */
+    int32_t cls_c;          /* channels of cls_feat (128)                                        */
+    const void* cls_w;      /* bf16 [cls_c] weight of the 1x1 cls conv (nc = 1)                  */
+    float cls_b;            /* its bias                                                          */
+} wt_head_level;
+
+typedef struct wt_post_params {
+    float conf_thres;       /* keep anchors with conf > conf_thres                    (0.1)      */
+    float iou_thres;        /* suppress when IoU > iou_thres                          (0.7)      */
+    int32_t max_det;        /* boxes kept per image                                   (1)        */
+    int32_t net_w, net_h;   /* letterboxed input size                                            */
+    int32_t img_w, img_h;   /* original image size boxes are scaled back to                      */
+    float gain;             /* scale_boxes gain = min(net_h/img_h, net_w/img_w)                  */
+    float pad_x, pad_y;     /* scale_boxes padding = round((net - img*gain)/2 - 0.1)             */
+} wt_post_params;
+
+/* out_boxes : f32 [n][max_det][6] = x1,y1,x2,y2 (original image px, clipped), conf, anchor index
+ * out_count : i32 [n] kept boxes per image (0 => the reference returns a NaN row)
+ * scratch   : >= wt_post_scratch_bytes(n, total_anchors) bytes                                  */
+int64_t wt_post_scratch_bytes(int n, int total_anchors);
+int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* p,
+                  float* out_boxes, int32_t* out_count, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K9  ResMLP position predictor                                                              */
+/*   replaces WormPredictor.forward / RMLP.forward (wtracker/neural/mlp.py:47-48,176-188)      */
+/*   as called by MLPController.provide_movement_vector (mlp_controllers.py:59)                */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct wt_resmlp_desc {
+    int32_t in_dim, hidden, out_dim;  /* 28, 40, 2                                               */
+    int32_t n_blocks, block_len;      /* 4 blocks of block_len=4 layers                          */
+    int32_t block_dims[8];            /* output width of each layer in a block (10,4,10,40)      */
+    /* weights: f32 device blob, BN folded, layers in execution order, each [out][in] then [out] */
+    const float* weights;
+    int32_t n_weights;                /* floats in the blob                                      */
+} wt_resmlp_desc;
+/* x: f32 [n][in_dim] -> y: f32 [n][out_dim] */
+int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* K10  per-step bbox metrics                                                                 */
+/*   replaces ErrorCalculator.calculate_bbox_error / calculate_mse_error                       */
+/*   (wtracker/eval/error_calculator.py:163-195, 197-212); float64 like the reference          */
+/* ------------------------------------------------------------------------------------------ */
+int wt_bbox_error(const double* worm_xywh, const double* mic_xywh, double* err, int64_t n, void* stream);
+int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* test-only helpers (allocate + synchronise; never called by the product path)               */
+/* ------------------------------------------------------------------------------------------ */
+/* Runs one conv through the tcgen05 kernel and the scalar validation kernel on seeded data and
+ * returns the max abs difference (bf16 outputs) in *max_abs_diff; prints one line when verbose. */
+int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int k, int stride, int act,
+                     int with_residual, int out_f32, int verbose, double* max_abs_diff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTRACKER_B200_H */

@@ -1,0 +1,73 @@
+"""Runs wt_selftest_conv (tcgen05 conv vs scalar validation conv) over the YOLOv8s layer shapes.
+
+Each case runs in its own process under a timeout so a hung kernel cannot stall the whole sweep.
+Usage: python tools/gpu_conv_selftest.py [--quick] [--one b,h,w,cin,cout,k,s,act,res,f32]
+"""
+
+from __future__ import annotations
+
+import subprocess
+import sys
+import time
+
+CASES = [
+    # batch, h, w, cin, cout, k, stride, act, res, f32
+    (2, 16, 16, 64, 64, 1, 1, 0, 0, 0),      # smallest: 1x1, no act
+    (2, 16, 16, 64, 64, 1, 1, 1, 0, 0),      # + SiLU
+    (2, 16, 16, 64, 64, 3, 1, 1, 0, 0),      # 3x3 taps + zero padding
+    (2, 16, 16, 64, 64, 3, 1, 1, 1, 0),      # + residual
+    (2, 16, 16, 64, 64, 1, 1, 0, 0, 1),      # f32 output
+    (2, 32, 32, 64, 128, 3, 2, 1, 0, 0),     # stride 2 parity views
+    (2, 16, 16, 32, 32, 3, 1, 1, 1, 0),      # BK=32 / BN=32 (SWIZZLE_64B everywhere)
+    (2, 32, 32, 32, 64, 3, 2, 1, 0, 0),      # layer 1 shape family
+    (2, 16, 16, 96, 64, 1, 1, 1, 0, 0),      # cin 96 -> BK 32
+    (2, 16, 16, 128, 256, 1, 1, 1, 0, 0),    # BN 256
+    (3, 20, 20, 256, 512, 3, 2, 1, 0, 0),    # ragged tiles, 2 N blocks, odd batch
+    (4, 20, 20, 256, 256, 3, 1, 1, 1, 0),    # 20x20 patch (4,4,8)
+    (2, 40, 40, 128, 128, 3, 1, 1, 0, 0),
+    (2, 80, 80, 64, 64, 3, 1, 1, 1, 0),
+    (2, 80, 80, 384, 128, 1, 1, 1, 0, 0),
+    (2, 20, 20, 1024, 512, 1, 1, 1, 0, 0),
+    (2, 80, 80, 64, 64, 1, 1, 0, 0, 1),      # head box logits f32
+    (8, 160, 160, 32, 64, 3, 2, 1, 0, 0),    # many tiles per CTA (persistence, phases)
+    (16, 80, 80, 128, 128, 3, 1, 1, 0, 0),
+]
+
+SNIPPET = """
+import ctypes, sys
+from wtracker_b200._lib import lib
+args = [int(v) for v in sys.argv[1].split(',')]
+d = ctypes.c_double(-1.0)
+rc = lib().wt_selftest_conv(*args, 1, ctypes.byref(d))
+if rc != 0:
+    print('ERROR', lib().wt_last_error().decode())
+    sys.exit(2)
+sys.exit(0 if d.value < 0.07 else 3)
+"""
+
+
+def main() -> int:
+    cases = CASES
+    if "--quick" in sys.argv:
+        cases = CASES[:6]
+    if "--one" in sys.argv:
+        cases = [tuple(int(v) for v in sys.argv[sys.argv.index("--one") + 1].split(","))]
+    failed = 0
+    for case in cases:
+        arg = ",".join(str(v) for v in case)
+        t0 = time.time()
+        try:
+            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, timeout=90)
+            status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
+            out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()
+        except subprocess.TimeoutExpired:
+            status, out = "TIMEOUT", ""
+        if status != "OK":
+            failed += 1
+        print(f"[{status}] {arg} ({time.time() - t0:.1f}s) {out}", flush=True)
+    print(f"{len(cases) - failed}/{len(cases)} conv selftests passed")
+    return 1 if failed else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

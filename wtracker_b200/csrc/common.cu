@@ -1,0 +1,90 @@
+// Error reporting, launch counter, device info and tensor-map encoding (driver entry point fetched
+// at run time so the library links against the CUDA runtime only).
+#include "../../include/wtracker_b200.h"
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+namespace wt {
+
+static thread_local std::string t_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const std::string& msg) { t_last_error = msg; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available (no CUDA driver / no GPU)");
+        return 1;
+    }
+    cuuint64_t gdims[5];
+    cuuint64_t gstr[4];
+    cuuint32_t gbox[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+    else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = fn(out, dtype, cuuint32_t(rank), base, gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[512];
+        snprintf(buf, sizeof buf,
+                 "cuTensorMapEncodeTiled failed (%d): rank %d base %p dims [%llu %llu %llu %llu] box [%u %u %u %u] "
+                 "stride0 %llu swizzle %d",
+                 int(r), rank, base, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                 (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                 rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+                 (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), swizzle_bytes);
+        set_error(buf);
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace wt
+
+extern "C" {
+
+const char* wt_last_error(void) { return wt::t_last_error.c_str(); }
+int wt_abi_version(void) { return WT_ABI_VERSION; }
+uint64_t wt_launch_count(void) { return wt::g_launch_count.load(); }
+
+int wt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    WT_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    WT_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// Shared host-side helpers: error reporting, launch counting, tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+namespace wt {
+
+void set_error(const std::string& msg);             // thread-local last error
+extern std::atomic<uint64_t> g_launch_count;        // kernels launched by this library
+
+#define WT_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::wt::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                            __FILE__ + ":" + std::to_string(__LINE__));                          \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+#define WT_REQUIRE(cond, msg)                                                              \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            ::wt::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +      \
+                            std::to_string(__LINE__));                                     \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+// count + check a kernel launch
+#define WT_LAUNCHED()                                  \
+    do {                                               \
+        ::wt::g_launch_count.fetch_add(1);             \
+        WT_CHECK_CUDA(cudaGetLastError());             \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Encodes a tiled tensor map (rank <= 5). dims/box in elements (innermost first), strides in bytes
+// for dims 1..rank-1. swizzle_bytes in {0, 32, 64, 128}. Returns 0 on success.
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* base, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+}  // namespace wt

@@ -1,0 +1,42 @@
+// Internal description of one convolution over NHWC buffers, shared by the tcgen05 implicit-GEMM
+// kernel (conv_tcgen05.cu), the scalar validation kernel and the small data-movement ops (ops_simt.cu).
+#pragma once
+#include "common.cuh"
+
+namespace wt {
+
+struct TensorView {      // NHWC view of (a channel slice of) an activation buffer
+    void* base;          // buffer base address ([batch][h][w][ctot])
+    int h, w;            // spatial size
+    int ctot;            // channels physically present in the buffer
+    int coff;            // first channel of the slice
+    int dtype;           // WT_DT_*
+};
+
+struct ConvDesc {
+    TensorView src, dst, res;   // res.base == nullptr -> no residual
+    int cin, cout, k, stride, act;
+    const __nv_bfloat16* w;     // [cout][k][k][cin]
+    const float* bias;          // [cout]
+    int batch;                  // images the buffers were sized for
+};
+
+// ---- tcgen05 path -------------------------------------------------------------------------
+struct ConvTcPlan;   // opaque: tensor maps + tiling, built once per layer
+int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out);
+void conv_tc_plan_destroy(ConvTcPlan* p);
+int conv_tc_launch(const ConvTcPlan* p, int n_images, int sm_count, cudaStream_t stream);
+
+// ---- scalar validation path ---------------------------------------------------------------
+int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream);
+
+// ---- other ops ----------------------------------------------------------------------------
+// first layer: u8 grey [n][h][w] -> bf16 NHWC [n][h/2][w/2][cout], 3x3 s2 p1, fp32 weights
+int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float* bias, int cout, int act,
+                 const TensorView& dst, int n_images, cudaStream_t stream);
+// SPPF: three chained 5x5/s1/p2 max-pools of src slice -> dst slices at dst.coff, +c, +2c
+int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream);
+// nearest 2x upsample of a channel slice into a slice of a (2h x 2w) buffer
+int upsample2x_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream);
+
+}  // namespace wt

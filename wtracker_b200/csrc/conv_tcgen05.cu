@@ -1,0 +1,506 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA, fused epilogue (bias + SiLU + residual + bf16/f32 cast) stored by TMA
+// straight into the (concat-)destination channel slice.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel @ tap, cin] * W[cout, tap, cin]
+//
+//   M tile  = 128 output pixels = a (tn x th x tw) patch of the NHWC output   (UMMA M = 128)
+//   N tile  = BN output channels                                              (UMMA N = BN)
+//   K block = BK input channels of one filter tap                             (UMMA K = 16)
+//
+// For every (tap, cin-block) the producer issues ONE 4-D TMA box load of the input shifted by the
+// tap offset; out-of-image pixels are zero-filled by TMA, which is exactly the conv zero padding,
+// and the box lands in smem as [128 pixels][BK channels] with the 128B/64B swizzle the UMMA
+// K-major descriptor expects.  Stride-2 convs use four parity views of the input (even/odd rows x
+// even/odd columns), so each tap is again a dense box.
+//
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer and
+// TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  The TMEM
+// accumulator is double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "../../include/wtracker_b200.h"
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace wt {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiBarrier = 1;          // named barrier id for the 4 epilogue warps
+constexpr int kStageBufBytes = 16384;   // one epilogue staging buffer: 128 rows x 128 B
+constexpr int kMaxStages = 8;
+
+struct ConvTcParams {
+    CUtensorMap tmA[4];   // input views (index = row parity * 2 + col parity for stride 2, else [0])
+    CUtensorMap tmB;      // weights [cout][k*k*cin]
+    CUtensorMap tmD;      // output slice
+    CUtensorMap tmR;      // residual slice (bf16)
+    const float* bias;
+    int tiles_x, tiles_y, tiles_n;   // pixel-tile grid
+    int n_blocks;                    // cout / BN
+    int tw, th, tn;                  // pixel patch, tw*th*tn == 128
+    int ksize, stride;
+    int cin, cin_blocks;             // cin / BK
+    int src_coff, dst_coff, res_coff;
+    int act, has_res, out_f32;
+    int num_tiles;
+};
+
+template <int BN, int BK>
+struct SmemLayout {
+    static constexpr int kRowBytes = BK * 2;
+    static constexpr int kABytes = kTileM * kRowBytes;
+    static constexpr int kBBytes = BN * kRowBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 512;  // staging + bias + barriers
+    static constexpr int kBudget = 232448 - 1024;                          // 227 KB minus alignment slack
+    static constexpr int kStagesRaw = (kBudget - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
+    static constexpr int kTotalBytes = kStages * kStageBytes + kFixedBytes + 1024;
+    static_assert(kStages >= 2, "not enough shared memory for a pipeline");
+};
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    using L = SmemLayout<BN, BK>;
+    constexpr int kStages = L::kStages;
+    constexpr int kRowBytes = L::kRowBytes;
+    constexpr uint32_t kTmemCols = 2 * BN;   // double-buffered accumulator (power of two >= 64)
+    static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                  // [stages][128][BK] bf16 (swizzled)
+    uint8_t* sB = smem + kStages * L::kABytes;           // [stages][BN][BK]  bf16 (swizzled)
+    uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 x 16 KB epilogue staging
+    float* sBias = reinterpret_cast<float*>(sStage + 2 * kStageBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
+    uint64_t* empty_bar = bars + kStages;            // [stages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * kStages;        // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]       epilogue -> MMA
+    uint64_t* res_bar = bars + 2 * kStages + 4;      // [2]       residual TMA -> epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.tmA[0]);
+        ptx::prefetch_tmap(&p.tmB);
+        ptx::prefetch_tmap(&p.tmD);
+        if (p.has_res) ptx::prefetch_tmap(&p.tmR);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&res_bar[i], 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int taps = p.ksize * p.ksize;
+    const int num_kb = taps * p.cin_blocks;
+    const int pad = p.ksize >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nblk = tile % p.n_blocks;
+                int m = tile / p.n_blocks;
+                const int xb = m % p.tiles_x;
+                m /= p.tiles_x;
+                const int yb = m % p.tiles_y;
+                const int nb = m / p.tiles_y;
+                const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                    int ax, ay, mapi;
+                    if (p.stride == 1) {
+                        ax = x0 + kw - pad;
+                        ay = y0 + kh - pad;
+                        mapi = 0;
+                    } else {   // stride 2, 3x3, pad 1: input row 2*oy+kh-1 -> parity view + offset
+                        ax = x0 + (kw == 0 ? -1 : 0);
+                        ay = y0 + (kh == 0 ? -1 : 0);
+                        mapi = ((kh != 1) ? 2 : 0) + ((kw != 1) ? 1 : 0);
+                    }
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                        ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                         p.src_coff + cb * BK, ax, ay, n0);
+                        ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
+                                         nblk * BN);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);   // epilogue has drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ab * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sA + stage * L::kABytes));
+                    const uint64_t b_desc = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB + stage * L::kBBytes));
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle span: start address += 2
+                        ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs finish
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int et = threadIdx.x - 64;        // 0..127
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
+        const bool store_thread = (et == 0);
+        // bf16 output: a staging row holds 64 channels (32 when BN == 32); f32 output: 32 channels
+        const int subs_per_unit = p.out_f32 ? 1 : (BN == 32 ? 1 : 2);
+        const int unit_ch = p.out_f32 ? 32 : (BN == 32 ? 32 : 64);
+        const bool rows64 = (!p.out_f32) && (BN == 32);   // 64-byte staging rows (SWIZZLE_64B)
+        const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
+        uint32_t unit_counter = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int nblk = tile % p.n_blocks;
+            int m = tile / p.n_blocks;
+            const int xb = m % p.tiles_x;
+            m /= p.tiles_x;
+            const int yb = m % p.tiles_y;
+            const int nb = m / p.tiles_y;
+            const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
+            const int ab = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+
+            for (int i = et; i < BN; i += kEpiThreads) sBias[i] = __ldg(p.bias + nblk * BN + i);
+
+            ptx::mbar_wait(&tfull_bar[ab], aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN;
+
+#pragma unroll 1
+            for (int sub = 0; sub < BN / 32; ++sub) {
+                const int sub_in_unit = sub % subs_per_unit;
+                const int unit = sub / subs_per_unit;
+                const int sb = unit_counter & 1;
+                uint8_t* stage_buf = sStage + sb * kStageBufBytes;
+                if (sub_in_unit == 0) {
+                    // the TMA store that last read this staging buffer must have finished reading
+                    if (store_thread) ptx::tma_store_wait_read<1>();
+                    ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                    if (p.has_res && store_thread) {
+                        ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
+                        ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * unit_ch, x0,
+                                         y0, n0);
+                    }
+                }
+                uint32_t acc[32];
+                ptx::tmem_ld_32x32(t_row + sub * 32, acc);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
+                    v[j] = p.act == WT_ACT_SILU ? silu(a) : a;
+                }
+                if (p.has_res && sub_in_unit == 0) ptx::mbar_wait(&res_bar[sb], (unit_counter >> 1) & 1);
+
+                if (p.out_f32) {
+                    // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B
+                    uint8_t* rowp = stage_buf + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = o;
+                    }
+                } else {
+                    // 32 bf16 = 64 B = 4 chunks of 16 B
+                    uint8_t* rowp;
+                    int cbase, xr;
+                    if (rows64) {
+                        rowp = stage_buf + row * 64;
+                        cbase = 0;
+                        xr = (row >> 1) & 3;
+                    } else {
+                        rowp = stage_buf + row * 128;
+                        cbase = sub_in_unit * 4;
+                        xr = row & 7;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4* dstp = reinterpret_cast<uint4*>(rowp + (((cbase + c) ^ xr) << 4));
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = v[8 * c + j];
+                        if (p.has_res) {
+                            const uint4 r = *dstp;
+                            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[2 * j] += __uint_as_float(rw[j] << 16);
+                                f[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+                            }
+                        }
+                        uint4 o;
+                        o.x = pack_bf16(f[0], f[1]);
+                        o.y = pack_bf16(f[2], f[3]);
+                        o.z = pack_bf16(f[4], f[5]);
+                        o.w = pack_bf16(f[6], f[7]);
+                        *dstp = o;
+                    }
+                }
+                if (sub == BN / 32 - 1) {
+                    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[ab]);
+                }
+                if (sub_in_unit == subs_per_unit - 1) {
+                    ptx::fence_proxy_async_smem();
+                    ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                    if (store_thread) {
+                        ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * unit_ch, x0, y0, n0);
+                        ptx::tma_store_commit();
+                    }
+                    ++unit_counter;
+                }
+            }
+        }
+        if (store_thread) ptx::tma_store_wait<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host
+
+struct ConvTcPlan {
+    ConvTcParams prm;
+    int bn, bk;
+    int pix_per_image_tiles;   // tiles_x * tiles_y
+};
+
+static void choose_patch(int w, int h, int batch, int* tw, int* th, int* tn) {
+    // (tw, th, tn) powers of two with product 128 minimising padded work; prefer wide rows
+    double best = 1e30;
+    for (int a = 128; a >= 1; a >>= 1) {
+        for (int b = 128 / a; b >= 1; b >>= 1) {
+            const int c = 128 / (a * b);
+            const double tiles = double(ceil_div(w, a)) * ceil_div(h, b) * ceil_div(batch, c);
+            const double cost = tiles * 128.0 / (double(w) * h * batch) + (c > 1 ? 1e-3 * c : 0.0) - 1e-5 * a;
+            if (cost < best) {
+                best = cost;
+                *tw = a;
+                *th = b;
+                *tn = c;
+            }
+        }
+    }
+}
+
+static int pick_bn(int cout) {
+    if (cout % 256 == 0) return 256;
+    if (cout % 128 == 0) return 128;
+    if (cout % 64 == 0) return 64;
+    if (cout % 32 == 0) return 32;
+    return 0;
+}
+
+int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
+    WT_REQUIRE(d.k == 1 || d.k == 3, "conv kernel size must be 1 or 3");
+    WT_REQUIRE(d.stride == 1 || (d.stride == 2 && d.k == 3), "stride 2 needs a 3x3 kernel");
+    WT_REQUIRE(d.src.dtype == WT_DT_BF16, "conv input must be bf16");
+    WT_REQUIRE(d.dst.dtype == WT_DT_BF16 || d.dst.dtype == WT_DT_F32, "conv output must be bf16 or f32");
+    const int bn = pick_bn(d.cout);
+    WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
+    const int bk = (d.cin % 64 == 0) ? 64 : 32;
+    WT_REQUIRE(d.cin % bk == 0, "cin must be a multiple of 32");
+    const int ho = d.dst.h, wo = d.dst.w;
+    if (d.stride == 1) {
+        WT_REQUIRE(d.src.h == ho && d.src.w == wo, "stride-1 conv keeps the spatial size");
+    } else {
+        WT_REQUIRE(d.src.h == 2 * ho && d.src.w == 2 * wo, "stride-2 conv halves an even spatial size");
+    }
+    const bool out_f32 = d.dst.dtype == WT_DT_F32;
+    WT_REQUIRE(!(out_f32 && d.res.base), "residual only with bf16 output");
+    // TMA needs 16-byte aligned global strides and base addresses
+    WT_REQUIRE((d.src.ctot * 2) % 16 == 0 && (d.src.coff * 2) % 16 == 0, "source channel alignment");
+    WT_REQUIRE((d.dst.ctot * (out_f32 ? 4 : 2)) % 16 == 0, "destination channel alignment");
+
+    ConvTcPlan* pl = new ConvTcPlan();
+    ConvTcParams& p = pl->prm;
+    pl->bn = bn;
+    pl->bk = bk;
+    choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
+    p.tiles_x = ceil_div(wo, p.tw);
+    p.tiles_y = ceil_div(ho, p.th);
+    p.tiles_n = ceil_div(d.batch, p.tn);
+    p.n_blocks = d.cout / bn;
+    p.ksize = d.k;
+    p.stride = d.stride;
+    p.cin = d.cin;
+    p.cin_blocks = d.cin / bk;
+    p.src_coff = d.src.coff;
+    p.dst_coff = d.dst.coff;
+    p.res_coff = d.res.base ? d.res.coff : 0;
+    p.act = d.act;
+    p.has_res = d.res.base ? 1 : 0;
+    p.out_f32 = out_f32 ? 1 : 0;
+    p.bias = d.bias;
+    p.num_tiles = 0;
+    pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
+
+    const int sw_in = bk * 2;   // swizzle span == K-block row bytes
+    int rc = 0;
+    const uint32_t box_a[4] = {uint32_t(bk), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+    if (d.stride == 1) {
+        const uint64_t dims[4] = {uint64_t(d.src.ctot), uint64_t(d.src.w), uint64_t(d.src.h), uint64_t(d.batch)};
+        const uint64_t str[3] = {uint64_t(d.src.ctot) * 2, uint64_t(d.src.ctot) * 2 * d.src.w,
+                                 uint64_t(d.src.ctot) * 2 * d.src.w * d.src.h};
+        rc |= encode_tmap(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.src.base, dims, str, box_a, sw_in);
+        for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    } else {
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                uint8_t* base = static_cast<uint8_t*>(d.src.base) + (size_t(py) * d.src.w + px) * d.src.ctot * 2;
+                const uint64_t dims[4] = {uint64_t(d.src.ctot), uint64_t(d.src.w / 2), uint64_t(d.src.h / 2),
+                                          uint64_t(d.batch)};
+                const uint64_t str[3] = {uint64_t(d.src.ctot) * 2 * 2, uint64_t(d.src.ctot) * 2 * d.src.w * 2,
+                                         uint64_t(d.src.ctot) * 2 * d.src.w * d.src.h};
+                rc |= encode_tmap(&p.tmA[py * 2 + px], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, str, box_a,
+                                  sw_in);
+            }
+    }
+    {
+        const uint64_t ktot = uint64_t(d.k) * d.k * d.cin;
+        const uint64_t dims[2] = {ktot, uint64_t(d.cout)};
+        const uint64_t str[1] = {ktot * 2};
+        const uint32_t box[2] = {uint32_t(bk), uint32_t(bn)};
+        rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
+                          sw_in);
+    }
+    {
+        const int es = out_f32 ? 4 : 2;
+        const int unit_ch = out_f32 ? 32 : (bn == 32 ? 32 : 64);
+        const int sw = unit_ch * es;   // 128 or 64
+        const uint64_t dims[4] = {uint64_t(d.dst.ctot), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
+        const uint64_t str[3] = {uint64_t(d.dst.ctot) * es, uint64_t(d.dst.ctot) * es * wo,
+                                 uint64_t(d.dst.ctot) * es * wo * ho};
+        const uint32_t box[4] = {uint32_t(unit_ch), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+        rc |= encode_tmap(&p.tmD, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                          d.dst.base, dims, str, box, sw);
+        if (d.res.base) {
+            if (d.res.h != ho || d.res.w != wo || d.res.dtype != WT_DT_BF16) {
+                set_error("residual must be a bf16 buffer of the output's spatial size");
+                rc = 1;
+            } else {
+                const uint64_t rdims[4] = {uint64_t(d.res.ctot), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
+                const uint64_t rstr[3] = {uint64_t(d.res.ctot) * 2, uint64_t(d.res.ctot) * 2 * wo,
+                                          uint64_t(d.res.ctot) * 2 * wo * ho};
+                rc |= encode_tmap(&p.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.res.base, rdims, rstr, box, sw);
+            }
+        } else {
+            p.tmR = p.tmD;
+        }
+    }
+    if (rc) {
+        delete pl;
+        return 1;
+    }
+    *out = pl;
+    return 0;
+}
+
+void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
+
+template <int BN, int BK>
+static int launch_inst(const ConvTcParams& prm, int grid, cudaStream_t stream) {
+    using L = SmemLayout<BN, BK>;
+    static bool configured = false;
+    if (!configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           L::kTotalBytes));
+        configured = true;
+    }
+    conv_tc_kernel<BN, BK><<<grid, kThreads, L::kTotalBytes, stream>>>(prm);
+    WT_LAUNCHED();
+    return 0;
+}
+
+int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
+    ConvTcParams prm = pl->prm;
+    const int tiles_n = ceil_div(n_images, prm.tn);
+    prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;
+    if (prm.num_tiles == 0) return 0;
+    const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+    const int key = pl->bn * 100 + pl->bk;
+    switch (key) {
+        case 25664: return launch_inst<256, 64>(prm, grid, stream);
+        case 12864: return launch_inst<128, 64>(prm, grid, stream);
+        case 6464:  return launch_inst<64, 64>(prm, grid, stream);
+        case 3264:  return launch_inst<32, 64>(prm, grid, stream);
+        case 25632: return launch_inst<256, 32>(prm, grid, stream);
+        case 12832: return launch_inst<128, 32>(prm, grid, stream);
+        case 6432:  return launch_inst<64, 32>(prm, grid, stream);
+        case 3232:  return launch_inst<32, 32>(prm, grid, stream);
+        default:
+            set_error("no conv_tc instantiation for this (BN, BK)");
+            return 1;
+    }
+}
+
+}  // namespace wt

@@ -1,0 +1,255 @@
+// Detector engine: executes a program of fused ops (wt_op) over caller-owned NHWC buffers.
+// Host-side bookkeeping only — all device memory (weights, workspace) belongs to the caller.
+#include "../../include/wtracker_b200.h"
+#include "conv.cuh"
+
+#include <vector>
+
+namespace wt {
+
+static int64_t dtype_size(int dt) { return dt == WT_DT_F32 ? 4 : (dt == WT_DT_U8 ? 1 : 2); }
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static int64_t buf_bytes(const wt_buf& b, int batch) {
+    return align_up(int64_t(batch) * b.h * b.w * b.c * dtype_size(b.dtype), 1024);
+}
+
+}  // namespace wt
+
+struct wt_engine {
+    std::vector<wt_buf> bufs;
+    std::vector<void*> buf_ptr;
+    std::vector<wt_op> ops;
+    std::vector<wt::ConvDesc> conv_desc;      // per op (valid for CONV)
+    std::vector<wt::ConvTcPlan*> conv_plan;   // per op (tcgen05 path)
+    int batch = 0;
+    int conv_impl = 0;
+    int sm_count = 0;
+    const uint8_t* weights = nullptr;
+    int64_t weight_bytes = 0;
+};
+
+using namespace wt;
+
+static TensorView view_of(const wt_engine* e, int id, int coff) {
+    TensorView v;
+    const wt_buf& b = e->bufs[id];
+    v.base = e->buf_ptr[id];
+    v.h = b.h;
+    v.w = b.w;
+    v.ctot = b.c;
+    v.coff = coff;
+    v.dtype = b.dtype;
+    return v;
+}
+
+extern "C" int64_t wt_engine_workspace_bytes(const wt_buf* bufs, int n_bufs, int batch) {
+    int64_t total = 0;
+    for (int i = 0; i < n_bufs; ++i) total += buf_bytes(bufs[i], batch);
+    return total + 1024;
+}
+
+extern "C" void wt_engine_destroy(wt_engine* e) {
+    if (!e) return;
+    for (ConvTcPlan* p : e->conv_plan)
+        if (p) conv_tc_plan_destroy(p);
+    delete e;
+}
+
+extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops, int n_ops, int batch,
+                                const void* weights, int64_t weight_bytes, void* workspace, int64_t workspace_bytes,
+                                int conv_impl, wt_engine** out) {
+    WT_REQUIRE(bufs && ops && weights && workspace && out, "null argument");
+    WT_REQUIRE(batch >= 1, "batch must be positive");
+    WT_REQUIRE(workspace_bytes >= wt_engine_workspace_bytes(bufs, n_bufs, batch), "workspace too small");
+    int cc_major = 0, sm = 0;
+    if (wt_device_info(&sm, &cc_major, nullptr)) return 1;
+    WT_REQUIRE(cc_major == 10, "wtracker_b200 needs an sm_100 (Blackwell B200) device");
+
+    wt_engine* e = new wt_engine();
+    e->batch = batch;
+    e->conv_impl = conv_impl;
+    e->sm_count = sm;
+    e->weights = static_cast<const uint8_t*>(weights);
+    e->weight_bytes = weight_bytes;
+    e->bufs.assign(bufs, bufs + n_bufs);
+    e->ops.assign(ops, ops + n_ops);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<int64_t>(workspace), 1024));
+    for (int i = 0; i < n_bufs; ++i) {
+        e->buf_ptr.push_back(ws);
+        ws += buf_bytes(bufs[i], batch);
+    }
+    e->conv_desc.resize(n_ops);
+    e->conv_plan.assign(n_ops, nullptr);
+
+    auto fail = [&](const char* msg, int i) {
+        set_error(std::string(msg) + " (op " + std::to_string(i) + ")");
+        wt_engine_destroy(e);
+        return 1;
+    };
+    for (int i = 0; i < n_ops; ++i) {
+        const wt_op& o = ops[i];
+        if (o.src < 0 || o.src >= n_bufs || o.dst < 0 || o.dst >= n_bufs) return fail("buffer id out of range", i);
+        if (o.res >= n_bufs) return fail("residual buffer id out of range", i);
+        if (o.kind == WT_OP_CONV) {
+            if (o.w_off < 0 || o.b_off < 0 || o.w_off + int64_t(o.cout) * o.k * o.k * o.cin * 2 > weight_bytes ||
+                o.b_off + int64_t(o.cout) * 4 > weight_bytes)
+                return fail("weight offsets out of range", i);
+            if (o.w_off % 16 != 0 || o.b_off % 4 != 0) return fail("weight offsets must be 16/4-byte aligned", i);
+            ConvDesc& d = e->conv_desc[i];
+            d.src = view_of(e, o.src, o.src_coff);
+            d.dst = view_of(e, o.dst, o.dst_coff);
+            if (o.res >= 0) d.res = view_of(e, o.res, o.res_coff);
+            else d.res = TensorView{nullptr, 0, 0, 0, 0, 0};
+            d.cin = o.cin;
+            d.cout = o.cout;
+            d.k = o.k;
+            d.stride = o.stride;
+            d.act = o.act;
+            d.w = reinterpret_cast<const __nv_bfloat16*>(e->weights + o.w_off);
+            d.bias = reinterpret_cast<const float*>(e->weights + o.b_off);
+            d.batch = batch;
+            if (o.src_coff + o.cin > e->bufs[o.src].c || o.dst_coff + o.cout > e->bufs[o.dst].c)
+                return fail("channel slice exceeds buffer", i);
+            if (conv_impl == 0) {
+                if (conv_tc_plan_create(d, &e->conv_plan[i])) {
+                    std::string m = wt_last_error();
+                    return fail(m.c_str(), i);
+                }
+            }
+        } else if (o.kind == WT_OP_CONV0) {
+            if (e->bufs[o.src].dtype != WT_DT_U8 || e->bufs[o.src].c != 1) return fail("conv0 source must be u8 grey", i);
+            if (o.w_off + int64_t(o.cout) * 9 * 4 > weight_bytes || o.b_off + int64_t(o.cout) * 4 > weight_bytes)
+                return fail("weight offsets out of range", i);
+        } else if (o.kind != WT_OP_SPPF_POOL && o.kind != WT_OP_UPSAMPLE2X) {
+            return fail("unknown op kind", i);
+        }
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" void* wt_engine_buffer(wt_engine* e, int id) {
+    if (!e || id < 0 || id >= int(e->bufs.size())) return nullptr;
+    return e->buf_ptr[id];
+}
+
+extern "C" int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op, void* stream_) {
+    WT_REQUIRE(e, "null engine");
+    WT_REQUIRE(n >= 0 && n <= e->batch, "n exceeds the engine batch");
+    WT_REQUIRE(first_op >= 0 && last_op <= int(e->ops.size()) && first_op <= last_op, "op range");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    for (int i = first_op; i < last_op; ++i) {
+        const wt_op& o = e->ops[i];
+        int rc = 0;
+        switch (o.kind) {
+            case WT_OP_CONV:
+                if (e->conv_impl == 0) rc = conv_tc_launch(e->conv_plan[i], n, e->sm_count, stream);
+                else rc = conv_simt_launch(e->conv_desc[i], n, stream);
+                break;
+            case WT_OP_CONV0:
+                rc = conv0_launch(static_cast<const uint8_t*>(e->buf_ptr[o.src]), e->bufs[o.src].h, e->bufs[o.src].w,
+                                  reinterpret_cast<const float*>(e->weights + o.w_off),
+                                  reinterpret_cast<const float*>(e->weights + o.b_off), o.cout, o.act,
+                                  view_of(e, o.dst, o.dst_coff), n, stream);
+                break;
+            case WT_OP_SPPF_POOL:
+                rc = sppf_pool_launch(view_of(e, o.src, o.src_coff), view_of(e, o.dst, o.dst_coff), o.cin, n, stream);
+                break;
+            case WT_OP_UPSAMPLE2X:
+                rc = upsample2x_launch(view_of(e, o.src, o.src_coff), view_of(e, o.dst, o.dst_coff), o.cin, n, stream);
+                break;
+            default:
+                set_error("unknown op kind");
+                rc = 1;
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ self-test
+namespace {
+__global__ void fill_bf16(__nv_bfloat16* p, size_t n, uint32_t seed, float scale) {
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = uint32_t(i) * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    p[i] = __float2bfloat16_rn((float(h & 0xFFFF) / 32768.f - 1.f) * scale);
+}
+__global__ void fill_f32(float* p, size_t n, uint32_t seed, float scale) {
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = uint32_t(i) * 2654435761u ^ seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    p[i] = (float(h & 0xFFFF) / 32768.f - 1.f) * scale;
+}
+__global__ void max_diff_kernel(const void* a, const void* b, size_t n, int f32, float* out_max, float* out_ref_max) {
+    size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float x, y;
+    if (f32) { x = static_cast<const float*>(a)[i]; y = static_cast<const float*>(b)[i]; }
+    else { x = __bfloat162float(static_cast<const __nv_bfloat16*>(a)[i]); y = __bfloat162float(static_cast<const __nv_bfloat16*>(b)[i]); }
+    float d = fabsf(x - y);
+    if (!(d == d)) d = 1e30f;
+    atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(d));
+    atomicMax(reinterpret_cast<int*>(out_ref_max), __float_as_int(fabsf(y)));
+}
+}  // namespace
+
+extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int k, int stride, int act,
+                                int with_residual, int out_f32, int verbose, double* max_abs_diff) {
+    int sm = 0, cc = 0;
+    if (wt_device_info(&sm, &cc, nullptr)) return 1;
+    const int ho = h / stride, wo = w / stride;
+    // source / destination sit inside wider buffers at a channel offset to exercise slicing
+    const int src_ct = cin + 64, src_off = 32, dst_ct = cout + 64, dst_off = 32;
+    const size_t n_src = size_t(batch) * h * w * src_ct, n_dst = size_t(batch) * ho * wo * dst_ct;
+    const size_t n_w = size_t(cout) * k * k * cin;
+    const int es = out_f32 ? 4 : 2;
+    __nv_bfloat16 *d_src = nullptr, *d_w = nullptr, *d_res = nullptr;
+    void *d_out_tc = nullptr, *d_out_ref = nullptr;
+    float *d_bias = nullptr, *d_stats = nullptr;
+    WT_CHECK_CUDA(cudaMalloc(&d_src, n_src * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_w, n_w * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_res, n_dst * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_out_tc, n_dst * es));
+    WT_CHECK_CUDA(cudaMalloc(&d_out_ref, n_dst * es));
+    WT_CHECK_CUDA(cudaMalloc(&d_bias, cout * 4));
+    WT_CHECK_CUDA(cudaMalloc(&d_stats, 8));
+    WT_CHECK_CUDA(cudaMemset(d_out_tc, 0, n_dst * es));
+    WT_CHECK_CUDA(cudaMemset(d_out_ref, 0, n_dst * es));
+    WT_CHECK_CUDA(cudaMemset(d_stats, 0, 8));
+    fill_bf16<<<unsigned((n_src + 255) / 256), 256>>>(d_src, n_src, 1u, 1.0f);
+    fill_bf16<<<unsigned((n_w + 255) / 256), 256>>>(d_w, n_w, 2u, 1.0f / sqrtf(float(k * k * cin)));
+    fill_bf16<<<unsigned((n_dst + 255) / 256), 256>>>(d_res, n_dst, 3u, 1.0f);
+    fill_f32<<<unsigned((cout + 255) / 256), 256>>>(d_bias, cout, 4u, 0.5f);
+    ConvDesc d;
+    d.src = TensorView{d_src, h, w, src_ct, src_off, WT_DT_BF16};
+    d.dst = TensorView{d_out_tc, ho, wo, dst_ct, dst_off, out_f32 ? WT_DT_F32 : WT_DT_BF16};
+    d.res = with_residual ? TensorView{d_res, ho, wo, dst_ct, dst_off, WT_DT_BF16} : TensorView{nullptr, 0, 0, 0, 0, 0};
+    d.cin = cin; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
+    d.w = d_w; d.bias = d_bias; d.batch = batch;
+    ConvTcPlan* plan = nullptr;
+    int rc = conv_tc_plan_create(d, &plan);
+    if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);
+    if (plan) conv_tc_plan_destroy(plan);
+    if (!rc) {
+        ConvDesc r = d;
+        r.dst.base = d_out_ref;
+        rc = conv_simt_launch(r, batch, 0);
+    }
+    float stats[2] = {0, 0};
+    if (!rc) {
+        max_diff_kernel<<<unsigned((n_dst + 255) / 256), 256>>>(d_out_tc, d_out_ref, n_dst, out_f32, d_stats, d_stats + 1);
+        cudaError_t e1 = cudaDeviceSynchronize();
+        if (e1 != cudaSuccess) { set_error(std::string("selftest kernel failed: ") + cudaGetErrorString(e1)); rc = 1; }
+        else cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_src); cudaFree(d_w); cudaFree(d_res); cudaFree(d_out_tc); cudaFree(d_out_ref); cudaFree(d_bias); cudaFree(d_stats);
+    if (rc) return rc;
+    if (max_abs_diff) *max_abs_diff = stats[0];
+    if (verbose)
+        printf("selftest_conv b%d %dx%d cin%d cout%d k%d s%d act%d res%d f32%d : max|diff| %.5g (ref max %.4g)\n", batch, h, w,
+               cin, cout, k, stride, act, with_residual, out_f32, stats[0], stats[1]);
+    return 0;
+}

@@ -1,0 +1,240 @@
+// CUDA-core ops of the detector program: the first layer (u8 grey -> 32 ch, direct 3x3/s2 conv),
+// the SPPF max-pool chain, nearest 2x upsampling into a concat slice, and a scalar convolution used
+// only to validate the tcgen05 kernel (tests / WT conv_impl=1).
+#include "../../include/wtracker_b200.h"
+#include "conv.cuh"
+
+namespace wt {
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// ------------------------------------------------------------------ scalar validation conv
+__global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sct, int scoff,
+                                 void* __restrict__ dst, int dh, int dw, int dct, int dcoff, int dst_f32,
+                                 const __nv_bfloat16* __restrict__ res, int rct, int rcoff,
+                                 const __nv_bfloat16* __restrict__ wgt, const float* __restrict__ bias, int cin,
+                                 int cout, int k, int stride, int act, long long total) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int co = int(idx % cout);
+    long long pix = idx / cout;
+    const int x = int(pix % dw);
+    pix /= dw;
+    const int y = int(pix % dh);
+    const int n = int(pix / dh);
+    const int pad = k / 2;
+    float acc = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+        const int iy = y * stride + kh - pad;
+        if (iy < 0 || iy >= sh) continue;
+        for (int kw = 0; kw < k; ++kw) {
+            const int ix = x * stride + kw - pad;
+            if (ix < 0 || ix >= sw) continue;
+            const __nv_bfloat16* ip = src + ((size_t(n) * sh + iy) * sw + ix) * sct + scoff;
+            const __nv_bfloat16* wp = wgt + ((size_t(co) * k + kh) * k + kw) * cin;
+            for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(ip[c]), __bfloat162float(wp[c]), acc);
+        }
+    }
+    float v = acc + bias[co];
+    if (act == WT_ACT_SILU) v = silu_f(v);
+    const size_t opix = (size_t(n) * dh + y) * dw + x;
+    if (res) v += __bfloat162float(res[opix * rct + rcoff + co]);
+    if (dst_f32) static_cast<float*>(dst)[opix * dct + dcoff + co] = v;
+    else static_cast<__nv_bfloat16*>(dst)[opix * dct + dcoff + co] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------ first layer
+// One thread per output pixel; weights (grey-folded, /255 folded) broadcast from shared memory.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
+                                                    const float* __restrict__ w9, const float* __restrict__ bias,
+                                                    int act, __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
+                                                    long long total) {
+    __shared__ float sw[COUT * 9];
+    __shared__ float sb[COUT];
+    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) sw[i] = w9[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ho = h / 2, wo = w / 2;
+    const int x = int(idx % wo);
+    const int y = int((idx / wo) % ho);
+    const int n = int(idx / (long long)(wo * ho));
+    const uint8_t* img = src + size_t(n) * h * w;
+    float in[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int iy = 2 * y + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ix = 2 * x + kw - 1;
+            const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+            in[kh * 3 + kw] = ok ? float(__ldg(img + size_t(iy) * w + ix)) : 0.f;
+        }
+    }
+    __nv_bfloat16* out = dst + size_t(idx) * dct + dcoff;
+#pragma unroll
+    for (int g = 0; g < COUT / 8; ++g) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* wp = sw + (g * 8 + j) * 9;
+            float a = sb[g * 8 + j];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) a = fmaf(in[t], wp[t], a);
+            o[j] = act == WT_ACT_SILU ? silu_f(a) : a;
+        }
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2);
+        pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(out + g * 8) = pk;
+    }
+}
+
+// ------------------------------------------------------------------ SPPF pooling chain
+// One CTA per (image, 32-channel group).  The slice lives in shared memory; each 5x5 max-pool is a
+// horizontal then a vertical 5-tap max (out-of-image taps ignored == -inf padding).
+constexpr int kPoolCg = 32;
+__global__ void __launch_bounds__(256) sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
+                                                        __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c,
+                                                        int h, int w) {
+    extern __shared__ __nv_bfloat162 pool_smem[];
+    const int hw = h * w;
+    __nv_bfloat162* cur = pool_smem;                      // [hw][16] pairs
+    __nv_bfloat162* tmp = pool_smem + hw * (kPoolCg / 2);
+    const int n = blockIdx.y;
+    const int c0 = blockIdx.x * kPoolCg;
+    const int items = hw * (kPoolCg / 2);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
+        cur[i] = *reinterpret_cast<const __nv_bfloat162*>(src + (size_t(n) * hw + pix) * sct + scoff + c0 + 2 * cp);
+    }
+    __syncthreads();
+    for (int round = 0; round < 3; ++round) {
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {
+            const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
+            const int y = pix / w, x = pix % w;
+            __nv_bfloat162 m = cur[i];
+            for (int d = -2; d <= 2; ++d) {
+                const int xx = x + d;
+                if (d != 0 && xx >= 0 && xx < w) m = __hmax2(m, cur[(y * w + xx) * (kPoolCg / 2) + cp]);
+            }
+            tmp[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {
+            const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
+            const int y = pix / w, x = pix % w;
+            __nv_bfloat162 m = tmp[i];
+            for (int d = -2; d <= 2; ++d) {
+                const int yy = y + d;
+                if (d != 0 && yy >= 0 && yy < h) m = __hmax2(m, tmp[(yy * w + x) * (kPoolCg / 2) + cp]);
+            }
+            *reinterpret_cast<__nv_bfloat162*>(dst + (size_t(n) * hw + pix) * dct + dcoff + round * c + c0 + 2 * cp) = m;
+            // every thread only rewrites the element it just read at index i; the next round reads
+            // neighbours, so publish after the barrier below
+            cur[i] = m;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sct, int scoff,
+                                  __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c8, long long total) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = int(idx % c8);
+    long long pix = idx / c8;
+    const int dw = 2 * sw, dh = 2 * sh;
+    const int x = int(pix % dw);
+    pix /= dw;
+    const int y = int(pix % dh);
+    const int n = int(pix / dh);
+    const uint4 v =
+        *reinterpret_cast<const uint4*>(src + ((size_t(n) * sh + (y >> 1)) * sw + (x >> 1)) * sct + scoff + g * 8);
+    *reinterpret_cast<uint4*>(dst + ((size_t(n) * dh + y) * dw + x) * dct + dcoff + g * 8) = v;
+}
+
+}  // namespace
+
+int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream) {
+    WT_REQUIRE(d.src.dtype == WT_DT_BF16, "conv input must be bf16");
+    const long long total = (long long)n_images * d.dst.h * d.dst.w * d.cout;
+    if (total == 0) return 0;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    conv_simt_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(d.src.base), d.src.h, d.src.w, d.src.ctot, d.src.coff, d.dst.base, d.dst.h,
+        d.dst.w, d.dst.ctot, d.dst.coff, d.dst.dtype == WT_DT_F32 ? 1 : 0,
+        static_cast<const __nv_bfloat16*>(d.res.base), d.res.ctot, d.res.coff, d.w, d.bias, d.cin, d.cout, d.k,
+        d.stride, d.act, total);
+    WT_LAUNCHED();
+    return 0;
+}
+
+int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float* bias, int cout, int act,
+                 const TensorView& dst, int n_images, cudaStream_t stream) {
+    WT_REQUIRE(cout == 32 || cout == 16 || cout == 64, "conv0 supports 16/32/64 output channels");
+    WT_REQUIRE(h % 2 == 0 && w % 2 == 0, "conv0 needs an even input size");
+    WT_REQUIRE(dst.dtype == WT_DT_BF16 && dst.h == h / 2 && dst.w == w / 2, "conv0 destination shape");
+    WT_REQUIRE(dst.ctot % 8 == 0 && dst.coff % 8 == 0, "conv0 destination channel alignment");
+    const long long total = (long long)n_images * (h / 2) * (w / 2);
+    if (total == 0) return 0;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dst.base);
+    if (cout == 32)
+        conv0_kernel<32><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
+    else if (cout == 16)
+        conv0_kernel<16><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
+    else
+        conv0_kernel<64><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
+    WT_LAUNCHED();
+    return 0;
+}
+
+int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream) {
+    WT_REQUIRE(c % kPoolCg == 0, "SPPF channels must be a multiple of 32");
+    WT_REQUIRE(src.h == dst.h && src.w == dst.w, "SPPF keeps the spatial size");
+    WT_REQUIRE(src.dtype == WT_DT_BF16 && dst.dtype == WT_DT_BF16, "SPPF works on bf16");
+    const size_t smem = size_t(src.h) * src.w * kPoolCg * 2 * 2;
+    WT_REQUIRE(smem <= 200 * 1024, "SPPF feature map too large for the shared-memory pool kernel");
+    if (n_images == 0) return 0;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    dim3 grid(c / kPoolCg, n_images);
+    sppf_pool_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
+                                                  static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h,
+                                                  src.w);
+    WT_LAUNCHED();
+    return 0;
+}
+
+int upsample2x_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream) {
+    WT_REQUIRE(c % 8 == 0 && src.coff % 8 == 0 && dst.coff % 8 == 0 && src.ctot % 8 == 0 && dst.ctot % 8 == 0,
+               "upsample channel alignment");
+    WT_REQUIRE(dst.h == 2 * src.h && dst.w == 2 * src.w, "upsample doubles the spatial size");
+    const long long total = (long long)n_images * dst.h * dst.w * (c / 8);
+    if (total == 0) return 0;
+    const int threads = 256;
+    upsample2x_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(src.base), src.h, src.w, src.ctot, src.coff,
+        static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c / 8, total);
+    WT_LAUNCHED();
+    return 0;
+}
+
+}  // namespace wt

@@ -1,0 +1,314 @@
+// K6-K8: class confidence, confidence filter, DFL box decode, greedy NMS, scale_boxes.
+//
+// One CTA per image.  (a) every warp walks anchors and computes the class logit (a 1x1 conv of the
+// cls-branch features, fp32, or a ready-made logit), keeping anchors with sigmoid(logit) > conf;
+// (b) candidates are ordered by (confidence desc, anchor index asc) with a shared-memory bitonic
+// sort of 64-bit keys (or a single arg-max when max_det == 1); (c) only candidates are DFL-decoded;
+// (d) warp 0 runs the greedy NMS against the list of boxes kept so far (a box survives iff no kept
+// box overlaps it with IoU > thr — identical to torchvision.ops.nms on score-sorted boxes);
+// (e) kept boxes are mapped back to the camera view like ultralytics scale_boxes + clip_boxes.
+// Arithmetic is written with explicit round-to-nearest intrinsics so no FMA contraction changes
+// the comparisons the reference makes in fp32.
+#include "../../include/wtracker_b200.h"
+#include "common.cuh"
+
+namespace wt {
+namespace {
+
+constexpr int kMaxLevels = 4;
+constexpr int kPostThreads = 512;
+constexpr int kMaxKeep = 1024;
+constexpr int kMaxClsC = 1024;
+
+struct PostParams {
+    wt_head_level lv[kMaxLevels];
+    int level_start[kMaxLevels + 1];
+    int n_levels;
+    int total_anchors;
+    int sort_cap;   // power of two >= total_anchors
+    wt_post_params pp;
+    float* out_boxes;
+    int32_t* out_count;
+    float* sc_box;       // [n][A][4] candidate boxes in sorted order (xyxy, letterboxed px)
+    float* sc_conf;      // [n][A]
+    int32_t* sc_idx;     // [n][A]
+};
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__device__ __forceinline__ int level_of(const PostParams& p, int a) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i)
+        if (i < p.n_levels && a >= p.level_start[i]) l = i;
+    return l;
+}
+
+// expectation of softmax(logits[16]) over bins 0..15
+__device__ __forceinline__ float dfl_side(const float* lg) {
+    float m = lg[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, lg[i]);
+    float e[16], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        e[i] = expf(__fsub_rn(lg[i], m));
+        s = __fadd_rn(s, e[i]);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(e[i], s), float(i)));
+    return acc;
+}
+
+__device__ void decode_box(const PostParams& p, int img, int a, float* xyxy) {
+    const int l = level_of(p, a);
+    const wt_head_level& L = p.lv[l];
+    const int local = a - p.level_start[l];
+    const int hw = L.h * L.w;
+    float lg[64];
+    if (L.box_dtype == WT_DT_F32) {
+        const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(L.box) + (size_t(img) * hw + local) * 64);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 v = __ldg(src + i);
+            lg[4 * i] = v.x; lg[4 * i + 1] = v.y; lg[4 * i + 2] = v.z; lg[4 * i + 3] = v.w;
+        }
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(L.box) + (size_t(img) * hw + local) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 v = __ldg(src + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                lg[8 * i + 2 * j] = bf16_lo(w[j]);
+                lg[8 * i + 2 * j + 1] = bf16_hi(w[j]);
+            }
+        }
+    }
+    const float dl = dfl_side(lg), dt = dfl_side(lg + 16), dr = dfl_side(lg + 32), db = dfl_side(lg + 48);
+    const float ax = float(local % L.w) + 0.5f, ay = float(local / L.w) + 0.5f;
+    const float s = float(L.stride);
+    // dist2bbox(xywh=True) * stride, then xywh2xyxy — same op order as the reference decode
+    const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+    const float cxs = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), s), cys = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), s);
+    const float ws = __fmul_rn(__fsub_rn(x2, x1), s), hs = __fmul_rn(__fsub_rn(y2, y1), s);
+    const float hw2 = __fdiv_rn(ws, 2.f), hh2 = __fdiv_rn(hs, 2.f);
+    xyxy[0] = __fsub_rn(cxs, hw2);
+    xyxy[1] = __fsub_rn(cys, hh2);
+    xyxy[2] = __fadd_rn(cxs, hw2);
+    xyxy[3] = __fadd_rn(cys, hh2);
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+    const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr > thr;
+}
+
+__global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) {
+    extern __shared__ unsigned long long keys[];            // [sort_cap]
+    __shared__ float s_clsw[kMaxLevels * kMaxClsC / 4];      // fp32 copy of the cls weights (<= 4 x 256) — see host check
+    __shared__ int s_count;
+    __shared__ unsigned long long s_red[kPostThreads / 32];
+    __shared__ float4 s_keep[kMaxKeep];
+    __shared__ int s_keep_src[kMaxKeep];
+    __shared__ int s_nkeep;
+
+    const int img = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = p.total_anchors;
+
+    if (tid == 0) { s_count = 0; s_nkeep = 0; }
+    for (int l = 0; l < p.n_levels; ++l) {
+        if (p.lv[l].cls_feat) {
+            const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.lv[l].cls_w);
+            for (int c = tid; c < p.lv[l].cls_c; c += kPostThreads) s_clsw[l * (kMaxClsC / 4) + c] = __bfloat162float(w[c]);
+        }
+    }
+    __syncthreads();
+
+    // ---- (a) confidence + filter
+    for (int a = warp; a < A; a += kPostThreads / 32) {
+        const int l = level_of(p, a);
+        const wt_head_level& L = p.lv[l];
+        const int local = a - p.level_start[l];
+        const size_t pix = size_t(img) * L.h * L.w + local;
+        float logit;
+        if (L.cls_logit) {
+            logit = __ldg(L.cls_logit + pix);
+        } else {
+            const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(L.cls_feat) + pix * L.cls_c;
+            const float* w = s_clsw + l * (kMaxClsC / 4);
+            float acc = 0.f;
+            for (int c = lane * 4; c < L.cls_c; c += 128) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(f + c));
+                acc = fmaf(bf16_lo(v.x), w[c], acc);
+                acc = fmaf(bf16_hi(v.x), w[c + 1], acc);
+                acc = fmaf(bf16_lo(v.y), w[c + 2], acc);
+                acc = fmaf(bf16_hi(v.y), w[c + 3], acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            logit = acc + L.cls_b;
+        }
+        const float conf = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
+        if (lane == 0 && conf > p.pp.conf_thres) {
+            const int pos = atomicAdd(&s_count, 1);
+            keys[pos] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - unsigned(a));
+        }
+    }
+    __syncthreads();
+    const int n = s_count;
+    if (n == 0) {
+        if (tid == 0) p.out_count[img] = 0;
+        return;
+    }
+
+    float* cbox = p.sc_box + size_t(img) * A * 4;
+    float* cconf = p.sc_conf + size_t(img) * A;
+    int32_t* cidx = p.sc_idx + size_t(img) * A;
+    int n_sorted;
+
+    if (p.pp.max_det == 1) {
+        // ---- (b') arg-max: highest confidence, lowest anchor index on ties
+        unsigned long long best = 0;
+        for (int i = tid; i < n; i += kPostThreads) best = keys[i] > best ? keys[i] : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kPostThreads / 32; ++w) best = s_red[w] > best ? s_red[w] : best;
+            keys[0] = best;
+        }
+        __syncthreads();
+        n_sorted = 1;
+    } else {
+        // ---- (b) bitonic sort, descending
+        int P = 1;
+        while (P < n) P <<= 1;
+        for (int i = n + tid; i < P; i += kPostThreads) keys[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += kPostThreads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = keys[i], b = keys[ixj];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        n_sorted = n;
+    }
+
+    // ---- (c) decode candidates in sorted order
+    for (int i = tid; i < n_sorted; i += kPostThreads) {
+        const unsigned long long k = keys[i];
+        const int a = int(0xFFFFFFFFu - unsigned(k & 0xFFFFFFFFull));
+        float b[4];
+        decode_box(p, img, a, b);
+        cbox[4 * i] = b[0]; cbox[4 * i + 1] = b[1]; cbox[4 * i + 2] = b[2]; cbox[4 * i + 3] = b[3];
+        cconf[i] = __uint_as_float(unsigned(k >> 32));
+        cidx[i] = a;
+    }
+    __syncthreads();
+
+    // ---- (d) greedy NMS, warp 0
+    if (warp == 0) {
+        int nk = 0;
+        const int max_det = p.pp.max_det < kMaxKeep ? p.pp.max_det : kMaxKeep;
+        for (int i = 0; i < n_sorted && nk < max_det; ++i) {
+            const float4 bi = make_float4(cbox[4 * i], cbox[4 * i + 1], cbox[4 * i + 2], cbox[4 * i + 3]);
+            bool sup = false;
+            for (int j = lane; j < nk; j += 32) sup |= iou_gt(s_keep[j], bi, p.pp.iou_thres);
+            if (!__any_sync(0xffffffffu, sup)) {
+                if (lane == 0) { s_keep[nk] = bi; s_keep_src[nk] = i; }
+                ++nk;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) s_nkeep = nk;
+    }
+    __syncthreads();
+
+    // ---- (e) scale back to the camera view, clip, emit
+    const int nk = s_nkeep;
+    for (int k = tid; k < nk; k += kPostThreads) {
+        const float4 b = s_keep[k];
+        const int src = s_keep_src[k];
+        float x1 = __fdiv_rn(__fsub_rn(b.x, p.pp.pad_x), p.pp.gain), y1 = __fdiv_rn(__fsub_rn(b.y, p.pp.pad_y), p.pp.gain);
+        float x2 = __fdiv_rn(__fsub_rn(b.z, p.pp.pad_x), p.pp.gain), y2 = __fdiv_rn(__fsub_rn(b.w, p.pp.pad_y), p.pp.gain);
+        const float W = float(p.pp.img_w), H = float(p.pp.img_h);
+        x1 = fminf(fmaxf(x1, 0.f), W); x2 = fminf(fmaxf(x2, 0.f), W);
+        y1 = fminf(fmaxf(y1, 0.f), H); y2 = fminf(fmaxf(y2, 0.f), H);
+        float* o = p.out_boxes + (size_t(img) * p.pp.max_det + k) * 6;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        o[4] = cconf[src];
+        o[5] = float(cidx[src]);
+    }
+    if (tid == 0) p.out_count[img] = nk;
+}
+
+}  // namespace
+}  // namespace wt
+
+extern "C" int64_t wt_post_scratch_bytes(int n, int total_anchors) {
+    return int64_t(n) * total_anchors * (4 * 4 + 4 + 4) + 256;
+}
+
+extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* pp,
+                             float* out_boxes, int32_t* out_count, void* scratch, void* stream) {
+    using namespace wt;
+    WT_REQUIRE(levels && pp && out_boxes && out_count && scratch, "null argument");
+    WT_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "1..4 head levels");
+    WT_REQUIRE(pp->max_det >= 1 && pp->max_det <= kMaxKeep, "max_det must be in [1, 1024]");
+    PostParams p;
+    int total = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        p.lv[l] = levels[l];
+        p.level_start[l] = total;
+        total += levels[l].h * levels[l].w;
+        WT_REQUIRE(levels[l].box, "box logits missing");
+        WT_REQUIRE((levels[l].cls_feat != nullptr) != (levels[l].cls_logit != nullptr), "give cls_feat or cls_logit");
+        if (levels[l].cls_feat)
+            WT_REQUIRE(levels[l].cls_c % 4 == 0 && levels[l].cls_c <= kMaxClsC / 4 && levels[l].cls_w, "cls feature channels");
+    }
+    for (int l = n_levels; l <= kMaxLevels; ++l) p.level_start[l] = total;
+    p.n_levels = n_levels;
+    p.total_anchors = total;
+    int cap = 1;
+    while (cap < total) cap <<= 1;
+    p.sort_cap = cap;
+    const size_t smem = size_t(cap) * 8;
+    WT_REQUIRE(smem <= 160 * 1024, "too many anchors for the shared-memory candidate sort (max 20480)");
+    p.pp = *pp;
+    p.out_boxes = out_boxes;
+    p.out_count = out_count;
+    uint8_t* sc = static_cast<uint8_t*>(scratch);
+    p.sc_box = reinterpret_cast<float*>(sc);
+    p.sc_conf = reinterpret_cast<float*>(sc + size_t(n) * total * 16);
+    p.sc_idx = reinterpret_cast<int32_t*>(sc + size_t(n) * total * 20);
+    if (n == 0) return 0;
+    static size_t configured = 0;
+    if (smem > configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    post_kernel<<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    WT_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,131 @@
+// K9: batched ResMLP position predictor (BatchNorm folded into the linear layers on the host).
+//   x = relu(W_in x + b_in);  for each block: x = x + block(x), block = block_len x (linear + relu);
+//   y = W_out x + b_out                                  (wtracker/neural/mlp.py:144-188)
+// One sample per thread; the whole weight set (5.6 k / 20 k floats) sits in shared memory and is
+// read as warp-wide broadcasts; per-thread activation vectors live in shared memory with a
+// conflict-free [feature][thread] layout.  fp32 FMA throughout.
+#include "../../include/wtracker_b200.h"
+#include "common.cuh"
+
+namespace wt {
+namespace {
+
+constexpr int kMlpThreads = 128;
+constexpr int kLd = kMlpThreads + 1;   // padded leading dimension of the activation tiles
+
+struct MlpParams {
+    wt_resmlp_desc d;
+    const float* x;
+    float* y;
+    long long n;
+    int maxw;   // widest layer
+};
+
+__device__ __forceinline__ void dense(const float* __restrict__ w, const float* __restrict__ b, const float* in,
+                                      float* out, int nin, int nout, bool relu, int t) {
+    int o = 0;
+    for (; o + 4 <= nout; o += 4) {
+        float a0 = b[o], a1 = b[o + 1], a2 = b[o + 2], a3 = b[o + 3];
+        const float* w0 = w + size_t(o) * nin;
+        for (int i = 0; i < nin; ++i) {
+            const float v = in[i * kLd + t];
+            a0 = fmaf(v, w0[i], a0);
+            a1 = fmaf(v, w0[nin + i], a1);
+            a2 = fmaf(v, w0[2 * nin + i], a2);
+            a3 = fmaf(v, w0[3 * nin + i], a3);
+        }
+        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+        out[o * kLd + t] = a0; out[(o + 1) * kLd + t] = a1; out[(o + 2) * kLd + t] = a2; out[(o + 3) * kLd + t] = a3;
+    }
+    for (; o < nout; ++o) {
+        float a = b[o];
+        const float* w0 = w + size_t(o) * nin;
+        for (int i = 0; i < nin; ++i) a = fmaf(in[i * kLd + t], w0[i], a);
+        out[o * kLd + t] = relu ? fmaxf(a, 0.f) : a;
+    }
+}
+
+__global__ void __launch_bounds__(kMlpThreads) resmlp_kernel(const MlpParams p) {
+    extern __shared__ float mlp_smem[];
+    float* sw = mlp_smem;                              // weights
+    float* xs = sw + ((p.d.n_weights + 31) & ~31);     // residual stream  [maxw][kLd]
+    float* t0 = xs + p.maxw * kLd;                     // scratch A
+    float* t1 = t0 + p.maxw * kLd;                     // scratch B
+    const int t = threadIdx.x;
+    for (int i = t; i < p.d.n_weights; i += kMlpThreads) sw[i] = __ldg(p.d.weights + i);
+
+    const long long base = (long long)blockIdx.x * kMlpThreads;
+    const int valid = int(min((long long)kMlpThreads, p.n - base));
+    const int ind = p.d.in_dim;
+    for (int i = t; i < kMlpThreads * ind; i += kMlpThreads) {
+        const int s = i / ind, f = i - s * ind;
+        t0[f * kLd + s] = s < valid ? __ldg(p.x + base * ind + i) : 0.f;
+    }
+    __syncthreads();
+
+    const float* w = sw;
+    const int H = p.d.hidden;
+    dense(w, w + H * ind, t0, xs, ind, H, true, t);
+    w += H * ind + H;
+    for (int blk = 0; blk < p.d.n_blocks; ++blk) {
+        const float* in = xs;
+        int nin = H;
+        float* bufs[2] = {t0, t1};
+        for (int l = 0; l < p.d.block_len; ++l) {
+            const int nout = p.d.block_dims[l];
+            float* out = bufs[l & 1];
+            dense(w, w + nout * nin, in, out, nin, nout, true, t);
+            w += nout * nin + nout;
+            in = out;
+            nin = nout;
+        }
+        for (int f = 0; f < H; ++f) xs[f * kLd + t] += in[f * kLd + t];
+    }
+    dense(w, w + p.d.out_dim * H, xs, t0, H, p.d.out_dim, false, t);
+    __syncthreads();
+    const int od = p.d.out_dim;
+    for (int i = t; i < valid * od; i += kMlpThreads) {
+        const int s = i / od, f = i - s * od;
+        p.y[base * od + i] = t0[f * kLd + s];
+    }
+}
+
+}  // namespace
+}  // namespace wt
+
+extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float* y, int64_t n, void* stream) {
+    using namespace wt;
+    WT_REQUIRE(d && x && y && d->weights, "null argument");
+    WT_REQUIRE(d->block_len >= 1 && d->block_len <= 8 && d->n_blocks >= 0, "block shape");
+    WT_REQUIRE(d->block_dims[d->block_len - 1] == d->hidden, "a block must map hidden -> hidden");
+    int maxw = d->in_dim > d->hidden ? d->in_dim : d->hidden;
+    long long expect = (long long)d->hidden * d->in_dim + d->hidden;
+    int nin = d->hidden;
+    long long per_block = 0;
+    for (int l = 0; l < d->block_len; ++l) {
+        per_block += (long long)d->block_dims[l] * nin + d->block_dims[l];
+        nin = d->block_dims[l];
+        if (nin > maxw) maxw = nin;
+    }
+    expect += per_block * d->n_blocks + (long long)d->out_dim * d->hidden + d->out_dim;
+    if (d->out_dim > maxw) maxw = d->out_dim;
+    WT_REQUIRE(expect == d->n_weights, "weight blob size does not match the layer description");
+    if (n == 0) return 0;
+    MlpParams p;
+    p.d = *d;
+    p.x = x;
+    p.y = y;
+    p.n = n;
+    p.maxw = maxw;
+    const size_t smem = (size_t((d->n_weights + 31) & ~31) + size_t(3) * maxw * kLd) * sizeof(float);
+    WT_REQUIRE(smem <= 220 * 1024, "ResMLP too large for the shared-memory kernel");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(resmlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    const long long blocks = (n + kMlpThreads - 1) / kMlpThreads;
+    resmlp_kernel<<<(unsigned)blocks, kMlpThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    WT_LAUNCHED();
+    return 0;
+}
