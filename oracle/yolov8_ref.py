@@ -203,14 +203,15 @@ class YoloV8s(nn.Module):
         self.nc = nc
         self.widths = c
 
-    def features(self, x):
-        """Returns the three raw head maps (B, 64+nc, h, w)."""
+    def features(self, x, taps: dict | None = None):
+        """Returns the three raw head maps (B, 64+nc, h, w); ``taps`` (if given) receives the
+        intermediate module outputs by name."""
         m = self.model
-        x = m[0](x)
-        x = m[1](x)
-        x = m[2](x)
-        x = m[3](x)
-        x4 = m[4](x)
+        x0 = m[0](x)
+        x1 = m[1](x0)
+        x2 = m[2](x1)
+        x3 = m[3](x2)
+        x4 = m[4](x3)
         x = m[5](x4)
         x6 = m[6](x)
         x = m[7](x6)
@@ -220,6 +221,8 @@ class YoloV8s(nn.Module):
         x15 = m[15](torch.cat((m[13](x12), x4), 1))
         x18 = m[18](torch.cat((m[16](x15), x12), 1))
         x21 = m[21](torch.cat((m[19](x18), x9), 1))
+        if taps is not None:
+            taps.update(m0=x0, m1=x1, m2=x2, m3=x3, x4=x4, x6=x6, x9=x9, x12=x12, x15=x15, x18=x18, x21=x21)
         return m[22]([x15, x18, x21])
 
     def forward(self, x):

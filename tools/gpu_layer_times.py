@@ -1,0 +1,39 @@
+"""Per-op timing of the detector program (CUDA events, warm, batch N): python tools/gpu_layer_times.py [batch] [imgsz]"""
+import sys
+import torch
+from wtracker_b200.detector.weights import synthetic_state_dict
+from wtracker_b200.detector.engine import DetectorEngine
+from wtracker_b200 import _lib as L
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+imgsz = int(sys.argv[2]) if len(sys.argv) > 2 else 640
+sd = synthetic_state_dict(0)
+eng = DetectorEngine(sd, (imgsz, imgsz), imgsz, batch=batch, max_det=1)
+eng.input_view.random_(0, 255)
+torch.cuda.synchronize()
+ops = eng.program.ops
+specs = {s.name: s for s in eng.arch.conv_specs()}
+for _ in range(3):
+    eng.forward(batch)
+torch.cuda.synchronize()
+def timeit(fn, iters=10):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[len(ts) // 2]
+total_ms = timeit(lambda: eng.forward(batch))
+tot_flop = 2 * eng.arch.macs_per_image(imgsz, imgsz) * batch
+print(f"whole forward: {total_ms:.3f} ms  -> {batch / total_ms * 1e3:.0f} img/s, {tot_flop / total_ms / 1e9:.1f} TFLOP/s")
+rows = []
+for i, o in enumerate(ops):
+    ms = timeit(lambda: eng.forward(batch, i, i + 1), 6)
+    h, w, c, _ = eng.program.bufs[o["dst"]]
+    flop = 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 * batch if o["kind"] in (0, 1) else 0
+    rows.append((ms, i, o["name"], o["cin"], o["cout"], o["k"], o["stride"], h, flop))
+s = sum(r[0] for r in rows)
+print(f"sum of per-op times: {s:.3f} ms")
+for ms, i, name, cin, cout, k, st, h, flop in rows:
+    print(f"{i:3d} {name:22s} {cin:5d}->{cout:4d} k{k} s{st} out{h:4d}  {ms*1e3:8.1f} us  {flop/ms/1e9 if flop else 0:7.1f} TF/s  {100*ms/s:5.1f}%")

@@ -1,0 +1,162 @@
+"""Runtime wrapper of the native detector: owns the torch tensors (weights, workspace, tables,
+outputs), hands raw pointers to the C ABI and exposes crop -> detect as one call.
+
+PyTorch is plumbing here (memory + streams); all arithmetic happens in libwtracker_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from wtracker_b200 import _lib as L
+from wtracker_b200.detector.arch import YoloV8Arch
+from wtracker_b200.detector.letterbox import Letterbox, letterbox_for, resize_tables
+from wtracker_b200.detector.program import Program, blob_tensor, build_program, ops_as_ctypes
+from wtracker_b200.detector.weights import infer_arch
+
+
+def _ptr(t: torch.Tensor | None) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DetectorEngine:
+    """YOLOv8 detector for views of a fixed size ``view_hw`` letterboxed to ``imgsz``.
+
+    detect_crops(): frames resident on the device + per-image (frame index, crop origin) ->
+    rows [x1, y1, x2, y2, conf, anchor] per image (view pixel coordinates) and a count per image.
+    """
+
+    def __init__(self, state_dict: dict[str, torch.Tensor], view_hw: tuple[int, int], imgsz: int = 384,
+                 batch: int = 16, conf: float = 0.1, iou: float = 0.7, max_det: int = 1, device: str = "cuda:0",
+                 conv_impl: int = 0, arch: YoloV8Arch | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("wtracker_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = L.lib()
+        self.device = torch.device(device)
+        self.arch = arch or infer_arch(state_dict)
+        self.lb: Letterbox = letterbox_for(view_hw, imgsz)
+        self.batch = int(batch)
+        self.conf, self.iou, self.max_det = float(conf), float(iou), int(max_det)
+        self.program: Program = build_program(state_dict, self.arch, self.lb.dst_h, self.lb.dst_w)
+
+        with torch.cuda.device(self.device):
+            self.weights = blob_tensor(self.program).to(self.device)
+            self._bufs, self._ops = ops_as_ctypes(self.program)
+            ws_bytes = self.lib.wt_engine_workspace_bytes(self._bufs, len(self.program.bufs), self.batch)
+            self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
+            handle = C.c_void_p()
+            L.check(self.lib.wt_engine_create(self._bufs, len(self.program.bufs), self._ops, len(self.program.ops),
+                                              self.batch, self.weights.data_ptr(), self.weights.numel(),
+                                              self.workspace.data_ptr(), ws_bytes, conv_impl, C.byref(handle)),
+                    "wt_engine_create")
+            self.handle = handle
+            # letterbox tables
+            self._tables = {}
+            if self.lb.resample:
+                self._tables = {k: torch.from_numpy(v).to(self.device) for k, v in resize_tables(self.lb).items()}
+            self._lb_c = L.WtLetterbox(self.lb.src_w, self.lb.src_h, self.lb.dst_w, self.lb.dst_h, self.lb.new_w,
+                                       self.lb.new_h, self.lb.pad_left, self.lb.pad_top,
+                                       _ptr(self._tables.get("xofs")), _ptr(self._tables.get("xcoef")),
+                                       _ptr(self._tables.get("yofs")), _ptr(self._tables.get("ycoef")))
+            # post-process state
+            A = self.program.total_anchors
+            self.out_boxes = torch.zeros((self.batch, self.max_det, 6), dtype=torch.float32, device=self.device)
+            self.out_count = torch.zeros((self.batch,), dtype=torch.int32, device=self.device)
+            self.scratch = torch.zeros(self.lib.wt_post_scratch_bytes(self.batch, A), dtype=torch.uint8,
+                                       device=self.device)
+            levels = (L.WtHeadLevel * 3)()
+            for i, h in enumerate(self.program.head):
+                levels[i] = L.WtHeadLevel(self.buffer_ptr(h["box"]), self.buffer_ptr(h["cls_feat"]), None, h["h"],
+                                          h["w"], h["stride"], L.WT_DT_F32, self.arch.cls_c,
+                                          self.weights.data_ptr() + h["cls_w_off"], h["cls_b"])
+            self._levels = levels
+            pad_x, pad_y = self.lb.scale_pad
+            self._post = L.WtPostParams(self.conf, self.iou, self.max_det, self.lb.dst_w, self.lb.dst_h,
+                                        self.lb.src_w, self.lb.src_h, self.lb.gain, pad_x, pad_y)
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self.lib.wt_engine_destroy(h)
+            self.handle = None
+
+    def buffer_ptr(self, buf_id: int) -> int:
+        return self.lib.wt_engine_buffer(self.handle, buf_id)
+
+    def buffer_tensor(self, name_or_id, n: int | None = None) -> torch.Tensor:
+        """Copy of an activation buffer as a torch tensor [n, h, w, c] (debug / tests)."""
+        bid = name_or_id if isinstance(name_or_id, int) else self.program.buf_id(name_or_id)
+        h, w, c, dt = self.program.bufs[bid]
+        dtype = {L.WT_DT_BF16: torch.bfloat16, L.WT_DT_F32: torch.float32, L.WT_DT_U8: torch.uint8}[dt]
+        n = self.batch if n is None else n
+        nbytes = n * h * w * c * torch.empty((), dtype=dtype).element_size()
+        off = self.buffer_ptr(bid) - self.workspace.data_ptr()
+        return self.workspace[off: off + nbytes].view(dtype).view(n, h, w, c).clone()
+
+    @property
+    def input_view(self) -> torch.Tensor:
+        """The u8 network input buffer [batch, net_h, net_w] (a view into the workspace)."""
+        h, w, _, _ = self.program.bufs[0]
+        off = self.buffer_ptr(0) - self.workspace.data_ptr()
+        return self.workspace[off: off + self.batch * h * w].view(self.batch, h, w)
+
+    # ------------------------------------------------------------------ stages
+    def preprocess(self, frames: torch.Tensor, frame_idx: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor,
+                   n: int, out_f32: torch.Tensor | None = None) -> None:
+        """K1-K4 into the engine's input buffer (and optionally the fp32 NCHW reference tensor)."""
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous() and frames.dim() == 3
+        assert frame_idx.dtype == crop_x.dtype == crop_y.dtype == torch.int32
+        L.check(self.lib.wt_preprocess(frames.data_ptr(), frames.shape[0], frames.shape[1], frames.shape[2],
+                                       frame_idx.data_ptr(), crop_x.data_ptr(), crop_y.data_ptr(), n,
+                                       C.byref(self._lb_c), self.buffer_ptr(0), _ptr(out_f32), _stream()),
+                "wt_preprocess")
+
+    def forward(self, n: int, first_op: int = 0, last_op: int | None = None) -> None:
+        """K5: runs the conv program on the first n images of the input buffer."""
+        last = len(self.program.ops) if last_op is None else last_op
+        L.check(self.lib.wt_engine_forward(self.handle, n, first_op, last, _stream()), "wt_engine_forward")
+
+    def postprocess(self, n: int) -> None:
+        """K6-K8 into out_boxes / out_count."""
+        L.check(self.lib.wt_decode_nms(self._levels, 3, n, C.byref(self._post), self.out_boxes.data_ptr(),
+                                       self.out_count.data_ptr(), self.scratch.data_ptr(), _stream()),
+                "wt_decode_nms")
+
+    # ------------------------------------------------------------------ whole path
+    def detect_crops(self, frames: torch.Tensor, frame_idx: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor):
+        """Device-resident path: returns (boxes [n, max_det, 6], count [n]) device tensors (views into
+        engine-owned outputs; valid until the next call)."""
+        n = int(frame_idx.numel())
+        assert n <= self.batch
+        self.preprocess(frames, frame_idx, crop_x, crop_y, n)
+        self.forward(n)
+        self.postprocess(n)
+        return self.out_boxes[:n], self.out_count[:n]
+
+    def detect_views(self, views: list[np.ndarray]) -> tuple[np.ndarray, np.ndarray]:
+        """Host path: list of (h, w) u8 grey camera views -> (boxes [n, max_det, 6], count [n]) numpy."""
+        n = len(views)
+        h, w = self.lb.src_h, self.lb.src_w
+        boxes = np.zeros((n, self.max_det, 6), np.float32)
+        counts = np.zeros((n,), np.int32)
+        with torch.cuda.device(self.device):
+            for s in range(0, n, self.batch):
+                chunk = views[s: s + self.batch]
+                host = torch.from_numpy(np.ascontiguousarray(np.stack(chunk))).pin_memory()
+                assert host.shape[1:] == (h, w), f"views must be {(h, w)}, got {tuple(host.shape[1:])}"
+                dev = host.to(self.device, non_blocking=True)
+                m = len(chunk)
+                idx = torch.arange(m, dtype=torch.int32, device=self.device)
+                zero = torch.zeros(m, dtype=torch.int32, device=self.device)
+                b, c = self.detect_crops(dev, idx, zero, zero)
+                boxes[s: s + m] = b.cpu().numpy()
+                counts[s: s + m] = c.cpu().numpy()
+        return boxes, counts

@@ -1,0 +1,186 @@
+"""Compiles a YOLOv8 state_dict into the op program the native engine executes
+(``wt_buf`` / ``wt_op`` in include/wtracker_b200.h) plus the packed weight blob.
+
+Layout decisions:
+  * activations are NHWC bf16; every Concat of the network is a *buffer*: producers store straight
+    into their channel slice (TMA store with a channel offset), so concatenation costs nothing;
+  * C2f: one buffer of (2+n)*c channels holds cv1's two halves and every bottleneck output; the
+    bottlenecks read/write channel slices of it, cv2 reads it whole;
+  * BatchNorm is folded into the conv weights; weights are bf16 [cout][kh][kw][cin] (K-major rows
+    for the UMMA B operand), biases fp32;
+  * the first conv sees three identical grey channels scaled by 1/255, so its weights are summed
+    over the input channels and divided by 255 on the host and it runs on the u8 image directly;
+  * the last 1x1 of the box branch writes fp32 (DFL is sensitive to logit rounding); the last 1x1
+    of the class branch (cout = nc = 1) is a dot product fused into the decode kernel.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from wtracker_b200 import _lib as L
+from wtracker_b200.detector.arch import REG_MAX, STRIDES, ConvSpec, YoloV8Arch
+from wtracker_b200.detector.weights import folded_conv
+
+
+@dataclass
+class Program:
+    arch: YoloV8Arch
+    net_h: int
+    net_w: int
+    bufs: list[tuple[int, int, int, int]] = field(default_factory=list)   # (h, w, c, dtype)
+    buf_names: list[str] = field(default_factory=list)
+    ops: list[dict] = field(default_factory=list)
+    blob: bytearray = field(default_factory=bytearray)
+    head: list[dict] = field(default_factory=list)    # per level: box buffer, cls feature buffer, cls w/b
+    taps: dict[str, tuple[int, int, int]] = field(default_factory=dict)   # module output name -> (buf, coff, c)
+
+    def buf_id(self, name: str) -> int:
+        return self.buf_names.index(name)
+
+    @property
+    def total_anchors(self) -> int:
+        return sum((self.net_h // s) * (self.net_w // s) for s in STRIDES)
+
+
+def _align(blob: bytearray, a: int) -> int:
+    pad = (-len(blob)) % a
+    blob.extend(b"\0" * pad)
+    return len(blob)
+
+
+def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net_w: int) -> Program:
+    assert net_h % 32 == 0 and net_w % 32 == 0, "network input must be a multiple of 32"
+    assert arch.nc == 1, "the fused class-logit path is written for single-class models (reference: single_cls)"
+    p = Program(arch, net_h, net_w)
+    specs = {s.name: s for s in arch.conv_specs()}
+    c = arch.c
+
+    def new_buf(name: str, down: int, ch: int, dtype: int = L.WT_DT_BF16) -> int:
+        p.bufs.append((net_h // down, net_w // down, ch, dtype))
+        p.buf_names.append(name)
+        return len(p.bufs) - 1
+
+    def add_weights(s: ConvSpec) -> tuple[int, int]:
+        w, b = folded_conv(sd, s)
+        w_off = _align(p.blob, 16)
+        wk = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)          # [cout][kh][kw][cin]
+        p.blob.extend(wk.view(torch.int16).numpy().tobytes())
+        b_off = _align(p.blob, 16)
+        p.blob.extend(b.float().numpy().tobytes())
+        return w_off, b_off
+
+    def conv(name: str, src: tuple[int, int], dst: tuple[int, int], res: tuple[int, int] | None = None):
+        s = specs[name]
+        w_off, b_off = add_weights(s)
+        p.ops.append(dict(kind=L.WT_OP_CONV, name=name, src=src[0], src_coff=src[1], dst=dst[0], dst_coff=dst[1],
+                          res=-1 if res is None else res[0], res_coff=0 if res is None else res[1], cin=s.cin,
+                          cout=s.cout, k=s.k, stride=s.stride, act=L.WT_ACT_SILU if s.bn_act else L.WT_ACT_NONE,
+                          w_off=w_off, b_off=b_off))
+
+    def c2f(idx: int, src: tuple[int, int], dst: tuple[int, int], down: int):
+        spec = arch.c2f[idx]
+        cc = spec.c
+        cat = new_buf(f"c2f{idx}.cat", down, (2 + spec.n) * cc)
+        tmp = new_buf(f"c2f{idx}.tmp", down, cc)
+        conv(f"model.{idx}.cv1", src, (cat, 0))
+        for i in range(spec.n):
+            x_in = (cat, (1 + i) * cc)
+            conv(f"model.{idx}.m.{i}.cv1", x_in, (tmp, 0))
+            conv(f"model.{idx}.m.{i}.cv2", (tmp, 0), (cat, (2 + i) * cc), res=x_in if spec.shortcut else None)
+        conv(f"model.{idx}.cv2", (cat, 0), dst)
+
+    # ---- buffers that are concat destinations of the neck
+    b_in = new_buf("input", 1, 1, L.WT_DT_U8)
+    b0 = new_buf("m0", 2, c[0])
+    b1 = new_buf("m1", 4, c[1])
+    b2 = new_buf("m2", 4, c[1])
+    b3 = new_buf("m3", 8, c[2])
+    cat14 = new_buf("cat14", 8, c[3] + c[2])      # [up(x12) | x4]
+    b5 = new_buf("m5", 16, c[3])
+    cat11 = new_buf("cat11", 16, c[4] + c[3])     # [up(x9)  | x6]
+    b7 = new_buf("m7", 32, c[4])
+    b8 = new_buf("m8", 32, c[4])
+    sppf = new_buf("sppf.cat", 32, 2 * c[4])      # [cv1 | pool5 | pool9 | pool13]
+    cat20 = new_buf("cat20", 32, c[3] + c[4])     # [x19 | x9]
+    cat17 = new_buf("cat17", 16, c[2] + c[3])     # [x16 | x12]
+    b15 = new_buf("m15", 8, c[2])
+    b18 = new_buf("m18", 16, c[3])
+    b21 = new_buf("m21", 32, c[4])
+
+    # ---- backbone
+    w0, bias0 = folded_conv(sd, specs["model.0"])
+    w_off = _align(p.blob, 16)
+    p.blob.extend((w0.sum(1) / 255.0).float().contiguous().numpy().tobytes())      # [cout][3][3]
+    b_off = _align(p.blob, 16)
+    p.blob.extend(bias0.float().numpy().tobytes())
+    p.ops.append(dict(kind=L.WT_OP_CONV0, name="model.0", src=b_in, src_coff=0, dst=b0, dst_coff=0, res=-1, res_coff=0,
+                      cin=1, cout=c[0], k=3, stride=2, act=L.WT_ACT_SILU, w_off=w_off, b_off=b_off))
+    conv("model.1", (b0, 0), (b1, 0))
+    c2f(2, (b1, 0), (b2, 0), 4)
+    conv("model.3", (b2, 0), (b3, 0))
+    c2f(4, (b3, 0), (cat14, c[3]), 8)             # x4
+    conv("model.5", (cat14, c[3]), (b5, 0))
+    c2f(6, (b5, 0), (cat11, c[4]), 16)            # x6
+    conv("model.7", (cat11, c[4]), (b7, 0))
+    c2f(8, (b7, 0), (b8, 0), 32)
+    conv("model.9.cv1", (b8, 0), (sppf, 0))
+    p.ops.append(dict(kind=L.WT_OP_SPPF_POOL, name="model.9.m", src=sppf, src_coff=0, dst=sppf, dst_coff=c[4] // 2,
+                      res=-1, res_coff=0, cin=c[4] // 2, cout=c[4] // 2, k=5, stride=1, act=0, w_off=0, b_off=0))
+    conv("model.9.cv2", (sppf, 0), (cat20, c[3]))  # x9
+
+    # ---- neck
+    def upsample(name, src, dst, ch):
+        p.ops.append(dict(kind=L.WT_OP_UPSAMPLE2X, name=name, src=src[0], src_coff=src[1], dst=dst[0], dst_coff=dst[1],
+                          res=-1, res_coff=0, cin=ch, cout=ch, k=1, stride=1, act=0, w_off=0, b_off=0))
+
+    upsample("model.10", (cat20, c[3]), (cat11, 0), c[4])
+    c2f(12, (cat11, 0), (cat17, c[2]), 16)        # x12
+    upsample("model.13", (cat17, c[2]), (cat14, 0), c[3])
+    c2f(15, (cat14, 0), (b15, 0), 8)              # x15
+    conv("model.16", (b15, 0), (cat17, 0))
+    c2f(18, (cat17, 0), (b18, 0), 16)             # x18
+    conv("model.19", (b18, 0), (cat20, 0))
+    c2f(21, (cat20, 0), (b21, 0), 32)             # x21
+
+    # ---- head
+    for lvl, (feat, down) in enumerate(((b15, 8), (b18, 16), (b21, 32))):
+        t1 = new_buf(f"head{lvl}.box1", down, arch.box_c)
+        t2 = new_buf(f"head{lvl}.box2", down, arch.box_c)
+        box = new_buf(f"head{lvl}.box", down, 4 * REG_MAX, L.WT_DT_F32)
+        u1 = new_buf(f"head{lvl}.cls1", down, arch.cls_c)
+        u2 = new_buf(f"head{lvl}.cls2", down, arch.cls_c)
+        conv(f"model.22.cv2.{lvl}.0", (feat, 0), (t1, 0))
+        conv(f"model.22.cv2.{lvl}.1", (t1, 0), (t2, 0))
+        conv(f"model.22.cv2.{lvl}.2", (t2, 0), (box, 0))
+        conv(f"model.22.cv3.{lvl}.0", (feat, 0), (u1, 0))
+        conv(f"model.22.cv3.{lvl}.1", (u1, 0), (u2, 0))
+        wc, bc = folded_conv(sd, specs[f"model.22.cv3.{lvl}.2"])
+        cw_off = _align(p.blob, 16)
+        p.blob.extend(wc.reshape(-1).to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+        p.head.append(dict(box=box, cls_feat=u2, cls_w_off=cw_off, cls_b=float(bc.reshape(-1)[0]), h=net_h // down,
+                           w=net_w // down, stride=STRIDES[lvl]))
+    _align(p.blob, 16)
+
+    p.taps = {
+        "x4": (cat14, c[3], c[2]), "x6": (cat11, c[4], c[3]), "x9": (cat20, c[3], c[4]),
+        "x12": (cat17, c[2], c[3]), "x15": (b15, 0, c[2]), "x18": (b18, 0, c[3]), "x21": (b21, 0, c[4]),
+        "m0": (b0, 0, c[0]), "m1": (b1, 0, c[1]), "m2": (b2, 0, c[1]), "m3": (b3, 0, c[2]),
+    }
+    return p
+
+
+def ops_as_ctypes(p: Program):
+    bufs = (L.WtBuf * len(p.bufs))(*[L.WtBuf(*b) for b in p.bufs])
+    ops = (L.WtOp * len(p.ops))()
+    for i, o in enumerate(p.ops):
+        ops[i] = L.WtOp(o["kind"], o["src"], o["src_coff"], o["dst"], o["dst_coff"], o["res"], o["res_coff"],
+                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"])
+    return bufs, ops
+
+
+def blob_tensor(p: Program) -> torch.Tensor:
+    return torch.from_numpy(np.frombuffer(bytes(p.blob), dtype=np.uint8).copy())
