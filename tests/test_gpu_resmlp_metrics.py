@@ -1,0 +1,83 @@
+"""K9 / K10 parity: ResMLP against the reference's known answers (rel 1e-3) and the per-step
+metrics against the reference's float64 results (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics_ref, resmlp_ref
+from wtracker_b200.paths import RESMLP_100, RESMLP_200
+
+pytestmark = pytest.mark.gpu
+REL = 1e-3   # BASELINE.json north_star: ResMLP outputs within 1e-3 relative
+
+
+def rel_err(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12)
+
+
+@pytest.mark.parametrize("tag,path", [("100", RESMLP_100), ("200", RESMLP_200)])
+def test_resmlp_known_answers(golden, tag, path):
+    from wtracker_b200.neural.engine import ResMLPEngine
+    from wtracker_b200.neural.mlp import load_worm_predictor
+
+    eng = ResMLPEngine(load_worm_predictor(path))
+    x = torch.from_numpy(golden[f"resmlp_{tag}_x"]).cuda()
+    y = eng.forward(x).cpu().numpy()
+    ref = golden[f"resmlp_{tag}_y"]
+    assert rel_err(y, ref) < REL
+    assert np.abs(y - ref).max() < 1e-3 * np.maximum(np.abs(ref), 1.0).max()
+    # the survey's 4-row KAT
+    torch.manual_seed(0)
+    x4 = (torch.randn(4, 28) * 5).cuda()
+    want = {"100": [[-1.5217, 7.5841], [-1.4177, 3.7792], [12.8905, 31.9347], [4.0825, 1.1607]],
+            "200": [[6.6595, 16.6938], [9.4990, 7.4832], [15.1734, 22.6223], [12.1566, 5.5336]]}[tag]
+    assert np.allclose(eng.forward(x4).cpu().numpy(), np.array(want), atol=2e-3)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 4096, 100_003])
+def test_resmlp_batches_match_oracle(n):
+    from wtracker_b200.neural.engine import ResMLPEngine
+    from wtracker_b200.neural.mlp import load_worm_predictor
+
+    model = load_worm_predictor(RESMLP_100)
+    eng = ResMLPEngine(model)
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((n, 28)) * 8).astype(np.float32)
+    x[:, :2] = 0
+    y = eng.forward(torch.from_numpy(x).cuda()).cpu().numpy()
+    m = min(n, 5000)
+    ref = resmlp_ref.resmlp_forward(model, x[:m])
+    assert rel_err(y[:m], ref) < REL
+    if n > m:   # size-independent property: rows are independent, so a permuted batch permutes the output
+        perm = rng.permutation(n)
+        y2 = eng.forward(torch.from_numpy(x[perm]).cuda()).cpu().numpy()
+        assert np.array_equal(y2, y[perm])
+    assert eng.forward_host(x[:1]).shape == (1, 2) and np.array_equal(eng.forward_host(x[:1]), y[:1])
+
+
+def test_metrics_bit_exact_vs_reference(golden):
+    from wtracker_b200.eval.error_calculator import ErrorCalculator
+
+    e = ErrorCalculator.calculate_bbox_error(golden["metric_worm"], golden["metric_mic"])
+    assert e.dtype == np.float64 and np.array_equal(e, golden["metric_bbox_error"], equal_nan=True)
+    m = ErrorCalculator.calculate_mse_error(golden["metric_worm"], golden["metric_mic"])
+    assert np.array_equal(m, golden["metric_mse_error"], equal_nan=True)
+
+
+def test_metrics_large_and_properties():
+    from wtracker_b200.eval.error_calculator import ErrorCalculator
+
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    worm = np.stack([rng.uniform(0, 1900, n), rng.uniform(0, 1000, n), rng.uniform(0, 30, n), rng.uniform(0, 30, n)], 1)
+    mic = worm + rng.normal(0, 10, (n, 4))
+    mic[:, 2:] = np.abs(mic[:, 2:])
+    worm[::1001] = np.nan
+    worm[7::997, 2] = 0
+    e = ErrorCalculator.calculate_bbox_error(worm, mic)
+    assert np.array_equal(e, metrics_ref.bbox_error(worm, mic), equal_nan=True)
+    ok = np.isfinite(e)
+    assert (e[ok] >= -1e-9).all() and (e[ok] <= 1 + 1e-9).all()   # fraction of the worm box outside the view
+    assert np.array_equal(ErrorCalculator.calculate_mse_error(worm, worm)[np.isfinite(worm).all(1)], np.zeros(int(np.isfinite(worm).all(1).sum())))
+    assert np.array_equal(ErrorCalculator.calculate_mse_error(worm, mic), metrics_ref.mse_error(worm, mic), equal_nan=True)
+    assert ErrorCalculator.calculate_bbox_error(np.zeros((0, 4)), np.zeros((0, 4))).shape == (0,)

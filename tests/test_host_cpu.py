@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference interface against golden vectors made by the real reference."""
+import numpy as np
+import pytest
+
+from wtracker_b200.sim import ExperimentConfig, SimController, Simulator, SineMotorController, TimingConfig, ViewController
+from wtracker_b200.sim.sim_controllers.csv_controller import CsvController
+from wtracker_b200.utils.bbox_utils import BoxConverter, BoxFormat, BoxUtils
+from wtracker_b200.utils.frame_reader import ArrayReader, DummyReader
+
+
+def make_timing(fps=60, ppm=90, im=100, pr=40, mv=50, cam=4.0, mic=0.32, n=1800):
+    exp = ExperimentConfig("t", n, fps, (1080, 1920), ppm, (960, 540))
+    return exp, TimingConfig(exp, im, pr, mv, (cam, cam), (mic, mic))
+
+
+def test_timing_config_derivations(golden):
+    for row in golden["timing"]:
+        fps, ppm, im, pr, mv, cam, mic = row[:7]
+        _, t = make_timing(fps, ppm, im, pr, mv, cam, mic)
+        got = [t.imaging_frame_num, t.pred_frame_num, t.moving_frame_num, t.camera_size_px[0], t.micro_size_px[0],
+               t.cycle_frame_num]
+        assert got == [int(v) for v in row[7:]]
+    assert not hasattr(t, "experiment_config")
+
+
+def test_sine_motor_steps(golden):
+    for row in golden["motor_steps"]:
+        n_mov, dx, dy = int(row[0]), int(row[1]), int(row[2])
+        _, t = make_timing(mv=n_mov * 1000 / 60 - 1)
+        assert t.moving_frame_num == n_mov
+        m = SineMotorController(t)
+        m.register_move(dx, dy)
+        got = [v for _ in range(n_mov) for v in m.step()]
+        assert got == [int(v) for v in row[3:3 + 2 * n_mov]]
+        assert sum(got[0::2]) == dx and sum(got[1::2]) == dy
+
+
+def test_view_controller_crops(golden):
+    frames = golden["view_frames"]
+    vc = ViewController(ArrayReader(frames), camera_size=(36, 36), micro_size=(5, 5), init_position=(96, 54))
+    for i, p in enumerate(golden["view_positions"]):
+        vc.seek(i % 3)
+        vc.set_position(*p)
+        assert np.array_equal(vc.camera_view(), golden["view_cam"][i])
+        assert np.array_equal(vc.micro_view(), golden["view_mic"][i])
+        boxes = list(vc.camera_position) + list(vc.micro_position) + list(vc.position)
+        assert [int(v) for v in boxes] == [int(v) for v in golden["view_boxes"][i]]
+        x0, y0 = vc.camera_crop_origin()
+        assert (x0, y0) == (int(vc.position[0]) - 18, int(vc.position[1]) - 18)
+
+
+def test_padded_read_matches_reference_layout():
+    frames = np.arange(2 * 6 * 8, dtype=np.uint8).reshape(2, 6, 8)
+    vc = ViewController(ArrayReader(frames), camera_size=(4, 4), micro_size=(2, 2), init_position=(3, 3))
+    vc.seek(1)
+    padded = vc.read()
+    assert padded.shape == (10, 12)
+    x, y, w, h = vc._calc_view_bbox(4, 4)
+    assert np.array_equal(padded[y:y + w, x:x + h], vc.camera_view())
+
+
+class _Recorder:
+    def __init__(self, inner):
+        self.inner, self.pos, self.vec = inner, [], []
+
+    def __getattr__(self, k):
+        return getattr(self.inner, k)
+
+    def on_camera_frame(self, sim):
+        self.pos.append(tuple(int(v) for v in sim.position))
+        return self.inner.on_camera_frame(sim)
+
+    def provide_movement_vector(self, sim):
+        v = self.inner.provide_movement_vector(sim)
+        self.vec.append((int(v[0]), int(v[1])))
+        return v
+
+
+@pytest.mark.parametrize("tag,im", [("200", 200), ("100", 100)])
+def test_simulator_csv_controller_trace(golden, tag, im):
+    exp, t = make_timing(im=im)
+    rec = _Recorder(CsvController(t, golden["trace_csv_table"]))
+    Simulator(t, exp, rec).run()
+    assert np.array_equal(np.array(rec.pos), golden[f"trace_csv_{tag}_pos"])
+    assert np.array_equal(np.array(rec.vec), golden[f"trace_csv_{tag}_vec"])
+
+
+def test_hook_order_and_dropped_last_cycle():
+    exp, t = make_timing(n=3 * 9 + 4)
+    calls = []
+
+    class Spy(SimController):
+        def begin_movement_prediction(self, sim):
+            calls.append(("pred", sim.frame_number))
+
+        def provide_movement_vector(self, sim):
+            calls.append(("vec", sim.frame_number))
+            return 3, -2
+
+        def _cycle_predict_all(self, sim):
+            return np.zeros((t.cycle_frame_num, 4))
+
+        def on_cycle_end(self, sim):
+            calls.append(("end", sim.frame_number))
+
+        def on_cycle_start(self, sim):
+            calls.append(("start", sim.frame_number))
+
+    Simulator(t, exp, Spy(t)).run()
+    assert t.cycle_frame_num == 9 and t.imaging_frame_num == 6 and t.pred_frame_num == 3
+    assert calls[:4] == [("start", 0), ("pred", 3), ("vec", 6), ("end", 9)]
+    assert [c for c in calls if c[0] == "end"] == [("end", 9), ("end", 18), ("end", 27)]   # cycle 3 never ends
+
+
+def test_dummy_reader_default_resolution():
+    exp, t = make_timing(n=20)
+    sim = Simulator(t, exp, CsvController(t, np.zeros((20, 4))))
+    assert sim.view._frame_reader.frame_shape == (1080 + 360, 1920 + 360, 3)
+    assert isinstance(sim.view._frame_reader, DummyReader)
+
+
+def test_bbox_utils(golden):
+    b = golden["disc_in"].copy()
+    d, legal = BoxUtils.discretize(b, (1080, 1920), BoxFormat.XYWH)
+    assert d.dtype == np.int32 and legal.dtype == bool
+    assert np.array_equal(d, golden["disc_out"]) and np.array_equal(legal, golden["disc_legal"])
+    assert np.all(b[np.isnan(golden["disc_in"]).any(1)] == 0)   # input mutated like the reference
+    clean = np.nan_to_num(golden["disc_in"])
+    assert np.array_equal(BoxUtils.center(clean), golden["center_out"])
+    assert np.array_equal(BoxUtils.round(clean, BoxFormat.XYWH), golden["round_out"])
+    xyxy = BoxConverter.to_xyxy(clean, BoxFormat.XYWH)
+    assert np.allclose(BoxConverter.to_xywh(xyxy, BoxFormat.XYXY), clean)
+    assert np.allclose(BoxConverter.to_yolo(clean, BoxFormat.XYWH)[:, :2], golden["center_out"])
+    assert BoxUtils.center(np.array([1.0, 2.0, 4.0, 6.0])).tolist() == [3.0, 5.0]

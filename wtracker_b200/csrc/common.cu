@@ -52,7 +52,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* bas
     else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = fn(out, dtype, cuuint32_t(rank), base, gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[512];
         snprintf(buf, sizeof buf,

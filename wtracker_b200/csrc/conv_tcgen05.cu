@@ -30,7 +30,7 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kEpiBarrier = 1;          // named barrier id for the 4 epilogue warps
 constexpr int kStageBufBytes = 16384;   // one epilogue staging buffer: 128 rows x 128 B
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 struct ConvTcParams {
     CUtensorMap tmA[4];   // input views (index = row parity * 2 + col parity for stride 2, else [0])
@@ -54,7 +54,7 @@ struct SmemLayout {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = BN * kRowBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 512;  // staging + bias + barriers
+    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 1024;  // staging + bias + barriers
     static constexpr int kBudget = 232448 - 1024;                          // 227 KB minus alignment slack
     static constexpr int kStagesRaw = (kBudget - kFixedBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
@@ -62,7 +62,13 @@ struct SmemLayout {
     static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
 
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU(v) = v * sigmoid(v) = h * tanh(h) + h with h = v / 2: ONE MUFU op (tanh.approx) per element
+// instead of two (ex2 + rcp) — the epilogue warps are MUFU/issue bound, not the tensor pipe.
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -219,7 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int ab = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
 
-            for (int i = et; i < BN; i += kEpiThreads) sBias[i] = __ldg(p.bias + nblk * BN + i);
+            // SiLU path keeps bias/2 so that h = acc * 0.5 + bias/2 is a single FFMA
+            for (int i = et; i < BN; i += kEpiThreads)
+                sBias[i] = __ldg(p.bias + nblk * BN + i) * (p.act == WT_ACT_SILU ? 0.5f : 1.0f);
 
             ptx::mbar_wait(&tfull_bar[ab], aphase);
             ptx::tc_fence_after();
@@ -245,10 +253,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 ptx::tmem_ld_32x32(t_row + sub * 32, acc);
                 ptx::tmem_ld_wait();
                 float v[32];
+                if (p.act == WT_ACT_SILU) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float a = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
-                    v[j] = p.act == WT_ACT_SILU ? silu(a) : a;
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = fmaf(__uint_as_float(acc[j]), 0.5f, sBias[sub * 32 + j]);
+                        v[j] = fmaf(h, tanh_fast(h), h);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
                 }
                 if (p.has_res && sub_in_unit == 0) ptx::mbar_wait(&res_bar[sb], (unit_counter >> 1) & 1);
 

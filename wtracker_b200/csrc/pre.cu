@@ -110,6 +110,7 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
                              const int32_t* crop_x, const int32_t* crop_y, int n, const wt_letterbox* lb,
                              uint8_t* out_u8, float* out_f32, void* stream) {
     using namespace wt;
+    if (n == 0) return 0;
     WT_REQUIRE(frames && frame_idx && crop_x && crop_y && lb, "null argument");
     WT_REQUIRE(out_u8 || out_f32, "no output requested");
     WT_REQUIRE(lb->new_w + lb->pad_left <= lb->dst_w && lb->new_h + lb->pad_top <= lb->dst_h, "letterbox geometry");

@@ -1,0 +1,5 @@
+from wtracker_b200.sim.sim_controllers.csv_controller import CsvController
+from wtracker_b200.sim.sim_controllers.mlp_controllers import MLPController
+from wtracker_b200.sim.sim_controllers.yolo_controller import YoloConfig, YoloController
+
+__all__ = ["CsvController", "MLPController", "YoloConfig", "YoloController"]
