@@ -140,6 +140,17 @@ int64_t wt_post_scratch_bytes(int n, int total_anchors);
 int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* p,
                   float* out_boxes, int32_t* out_count, void* scratch, void* stream);
 
+/* Rows of the tracking log from one batch of detections (the absolute-coordinate shift of
+ * LoggingController._log_cycle, wtracker/sim/sim_controllers/logging_controller.py:152-155, and the
+ * camera / microscope boxes of ViewController.camera_position / micro_position,
+ * wtracker/sim/view_controller.py:93-117):
+ *   worm_xywh[i] = best box of image i as (x, y, w, h) in FRAME pixels (NaN row when count == 0)
+ *   mic_xywh[i]  = microscope box centred like the camera view
+ * boxes: f32 [n][max_det][6], count: i32 [n] (outputs of wt_decode_nms); crop_x/y: camera-view origin. */
+int wt_track_rows(const float* boxes, const int32_t* count, int max_det, const int32_t* crop_x, const int32_t* crop_y,
+                  int cam_w, int cam_h, int mic_w, int mic_h, double* worm_xywh, double* mic_xywh, int64_t n,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* K9  ResMLP position predictor                                                              */
 /*   replaces WormPredictor.forward / RMLP.forward (wtracker/neural/mlp.py:47-48,176-188)      */
@@ -155,6 +166,14 @@ typedef struct wt_resmlp_desc {
 } wt_resmlp_desc;
 /* x: f32 [n][in_dim] -> y: f32 [n][out_dim] */
 int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float* y, int64_t n, void* stream);
+/* Network input rows from a bbox table — the gather + "relative to the first box" step of
+ * MLPController.provide_movement_vector (mlp_controllers.py:38-56) and CsvController.predict
+ * (csv_controller.py:25-37): for sample i and input offset j the row table[frame[i] + offsets[j]]
+ * (NaN when outside [0, table_rows)); x, y of every box minus x, y of box 0; float64 arithmetic,
+ * cast to f32.  valid[i] = 0 when any gathered value is non-finite (the controller then answers (0,0)).
+ * table: f64 [table_rows][4]; frame: i32 [n]; offsets: i32 [k] (device); x: f32 [n][4k]; valid: u8 [n]. */
+int wt_mlp_gather(const double* table, int64_t table_rows, const int32_t* frame, const int32_t* offsets, int k,
+                  float* x, uint8_t* valid, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K10  per-step bbox metrics                                                                 */

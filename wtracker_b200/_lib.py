@@ -90,7 +90,11 @@ SIGNATURES = {
     "wt_post_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "wt_decode_nms": (C.c_int, [C.POINTER(WtHeadLevel), C.c_int, C.c_int, C.POINTER(WtPostParams), C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wt_track_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_resmlp_forward": (C.c_int, [C.POINTER(WtResmlpDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "wt_mlp_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_void_p]),
     "wt_bbox_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mse_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_selftest_conv": (C.c_int, [C.c_int] * 11 + [C.POINTER(C.c_double)]),

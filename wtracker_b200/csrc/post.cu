@@ -263,8 +263,46 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     if (tid == 0) p.out_count[img] = nk;
 }
 
+__global__ void track_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ count, int max_det,
+                                  const int32_t* __restrict__ crop_x, const int32_t* __restrict__ crop_y, int cam_w,
+                                  int cam_h, int mic_w, int mic_h, double* __restrict__ worm, double* __restrict__ mic,
+                                  long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cx = double(crop_x[i]), cy = double(crop_y[i]);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double w0 = nan, w1 = nan, w2 = nan, w3 = nan;
+    if (count[i] > 0) {
+        const float* b = boxes + i * max_det * 6;
+        // xyxy -> xywh in float32 (BoxConverter.to_xywh on the fp32 result), then shifted by the
+        // camera origin in float64 (numpy promotes when the log adds the integer camera offset)
+        w0 = __dadd_rn(double(b[0]), cx);
+        w1 = __dadd_rn(double(b[1]), cy);
+        w2 = double(__fsub_rn(b[2], b[0]));
+        w3 = double(__fsub_rn(b[3], b[1]));
+    }
+    reinterpret_cast<double2*>(worm)[2 * i] = make_double2(w0, w1);
+    reinterpret_cast<double2*>(worm)[2 * i + 1] = make_double2(w2, w3);
+    // camera view origin = pos - cam//2  =>  pos = origin + cam//2 ; microscope origin = pos - mic//2
+    const double mx = cx + double(cam_w / 2) - double(mic_w / 2), my = cy + double(cam_h / 2) - double(mic_h / 2);
+    reinterpret_cast<double2*>(mic)[2 * i] = make_double2(mx, my);
+    reinterpret_cast<double2*>(mic)[2 * i + 1] = make_double2(double(mic_w), double(mic_h));
+}
+
 }  // namespace
 }  // namespace wt
+
+extern "C" int wt_track_rows(const float* boxes, const int32_t* count, int max_det, const int32_t* crop_x,
+                             const int32_t* crop_y, int cam_w, int cam_h, int mic_w, int mic_h, double* worm_xywh,
+                             double* mic_xywh, int64_t n, void* stream) {
+    using namespace wt;
+    if (n == 0) return 0;
+    WT_REQUIRE(boxes && count && crop_x && crop_y && worm_xywh && mic_xywh, "null argument");
+    track_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        boxes, count, max_det, crop_x, crop_y, cam_w, cam_h, mic_w, mic_h, worm_xywh, mic_xywh, n);
+    WT_LAUNCHED();
+    return 0;
+}
 
 extern "C" int64_t wt_post_scratch_bytes(int n, int total_anchors) {
     return int64_t(n) * total_anchors * (4 * 4 + 4 + 4) + 256;

@@ -90,8 +90,47 @@ __global__ void __launch_bounds__(kMlpThreads) resmlp_kernel(const MlpParams p) 
     }
 }
 
+__global__ void mlp_gather_kernel(const double* __restrict__ table, long long rows, const int32_t* __restrict__ frame,
+                                  const int32_t* __restrict__ offsets, int k, float* __restrict__ x,
+                                  uint8_t* __restrict__ valid, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int f = frame[i];
+    double x0 = 0.0, y0 = 0.0;
+    bool ok = true;
+    for (int j = 0; j < k; ++j) {
+        const long long r = (long long)f + offsets[j];
+        double b[4];
+        if (r >= 0 && r < rows) {
+            const double2 lo = reinterpret_cast<const double2*>(table)[2 * r], hi = reinterpret_cast<const double2*>(table)[2 * r + 1];
+            b[0] = lo.x; b[1] = lo.y; b[2] = hi.x; b[3] = hi.y;
+        } else {
+            b[0] = b[1] = b[2] = b[3] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        ok = ok && isfinite(b[0]) && isfinite(b[1]) && isfinite(b[2]) && isfinite(b[3]);
+        if (j == 0) { x0 = b[0]; y0 = b[1]; }
+        float* o = x + (i * k + j) * 4;
+        o[0] = float(__dsub_rn(b[0], x0));
+        o[1] = float(__dsub_rn(b[1], y0));
+        o[2] = float(b[2]);
+        o[3] = float(b[3]);
+    }
+    valid[i] = ok ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace wt
+
+extern "C" int wt_mlp_gather(const double* table, int64_t table_rows, const int32_t* frame, const int32_t* offsets,
+                             int k, float* x, uint8_t* valid, int64_t n, void* stream) {
+    using namespace wt;
+    if (n == 0) return 0;
+    WT_REQUIRE(table && frame && offsets && x && valid && k >= 1, "null argument");
+    mlp_gather_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, table_rows, frame,
+                                                                                                 offsets, k, x, valid, n);
+    WT_LAUNCHED();
+    return 0;
+}
 
 extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float* y, int64_t n, void* stream) {
     using namespace wt;

@@ -131,14 +131,26 @@ class DetectorEngine:
                 "wt_decode_nms")
 
     # ------------------------------------------------------------------ whole path
-    def detect_crops(self, frames: torch.Tensor, frame_idx: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor):
+    def detect_crops(self, frames: torch.Tensor, frame_idx: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor,
+                     marks: list | None = None):
         """Device-resident path: returns (boxes [n, max_det, 6], count [n]) device tensors (views into
-        engine-owned outputs; valid until the next call)."""
+        engine-owned outputs; valid until the next call).  ``marks`` (optional) receives a CUDA event
+        recorded after each stage (pre, forward, post) for stage timing."""
         n = int(frame_idx.numel())
         assert n <= self.batch
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+
         self.preprocess(frames, frame_idx, crop_x, crop_y, n)
+        mark()
         self.forward(n)
+        mark()
         self.postprocess(n)
+        mark()
         return self.out_boxes[:n], self.out_count[:n]
 
     def detect_views(self, views: list[np.ndarray]) -> tuple[np.ndarray, np.ndarray]:
