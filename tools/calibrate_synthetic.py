@@ -7,7 +7,7 @@ comparison, and nothing it "detects" relates to the worm).  So the two FINAL 1x1
 the stride-8 level are fitted in closed form (ridge regression on the random backbone's features
 over a few dozen synthetic worm views) to fire on the worm head and regress its 14x14 box:
   * class logit : class-balanced ridge fit of {head cell -> 1, far background -> 0} (the rest of the
-                  worm is "don't care"), affinely mapped so head cells sit near conf 0.62 and the
+                  worm is "do not care"), affinely mapped so head cells sit near conf 0.27 and the
                   highest background cell near conf 0.05
   * box logits  : per side a ridge fit of the DFL distance d (in stride units); the 16 bin logits
                   are -k*(i - d)^2 up to a per-side constant, i.e. LINEAR in d: 2*k*i*d - k*i^2
@@ -17,6 +17,7 @@ Everything is deterministic in the seed; uses the fp32 oracle model on the CPU.
     PYTHONPATH=. python tools/calibrate_synthetic.py [seed ...]
 """
 import json
+import os
 import math
 import sys
 
@@ -27,9 +28,10 @@ from oracle import yolov8_ref as O
 from wtracker_b200 import synth
 from wtracker_b200.detector.weights import CALIB_PATH, synthetic_state_dict
 
-import os
 
-POS_LOGIT, NEG_LOGIT = 0.5, -3.0
+
+POS_LOGIT, NEG_LOGIT = -1.0, -3.0
+DONT_CARE = int(os.environ.get("WT_DONT_CARE", "5"))   # cells around the head excluded from the fit
 N_VIEWS, VIEW, RIDGE, KAPPA = int(os.environ.get('WT_NVIEWS', '80')), 640, float(os.environ.get('WT_RIDGE', '1.0')), 2.0
 
 
@@ -48,7 +50,8 @@ def calibrate(seed: int) -> dict:
                 fi = int(rng.integers(0, 4000))     # keep the worm off the replicated frame border
             frame = synth.render_frame(fi, track, seed)
             off = rng.integers(-250, 251, 2)
-            pos = (int(track[fi, 0]) + int(off[0]), int(track[fi, 1]) + int(off[1]))
+            pos = (int(np.clip(track[fi, 0] + off[0], VIEW // 2, synth.FRAME_W - VIEW // 2)),
+                   int(np.clip(track[fi, 1] + off[1], VIEW // 2, synth.FRAME_H - VIEW // 2)))   # view inside the frame
             views.append(np.ascontiguousarray(synth.camera_view(frame, pos, VIEW)))
             hc.append((track[fi, 0] - (pos[0] - VIEW // 2), track[fi, 1] - (pos[1] - VIEW // 2)))
         taps = {}
@@ -63,14 +66,14 @@ def calibrate(seed: int) -> dict:
     n, gh, gw, _ = fc.shape
 
     # ---- class logit ------------------------------------------------------------------------
-    # head cell -> 1, far background -> 0; the rest of the worm (cells within 12 of the head) is
-    # "don't care" so the fit is not asked to tell the head from its own body
+    # head cell -> 1, everything else (background, body, tail) -> 0; the 5x5 cells around the head
+    # are "don't care" so the fit is not asked for a one-cell-sharp response
     target = torch.zeros(n, gh, gw, dtype=torch.float64)
     care = torch.ones(n, gh, gw, dtype=torch.bool)
     pos_cells = []
     for k, (hx, hy) in enumerate(heads):
         cx, cy = int(hx // 8), int(hy // 8)
-        care[k, max(cy - 12, 0): cy + 13, max(cx - 12, 0): cx + 13] = False
+        care[k, max(cy - DONT_CARE, 0): cy + DONT_CARE + 1, max(cx - DONT_CARE, 0): cx + DONT_CARE + 1] = False
         if 1 <= cx < gw - 1 and 1 <= cy < gh - 1:
             target[k, cy, cx] = 1.0
             care[k, cy, cx] = True
@@ -86,8 +89,14 @@ def calibrate(seed: int) -> dict:
     score = Xc @ w
     s_pos = float(score[t > 0].mean())
     s_neg = float(score[t == 0].max())
-    # head cells -> logit +0.5 on average (conf 0.62), the highest background cell -> logit -3 (conf 0.047);
+    # head cells -> logit -1 on average (conf 0.27), the highest background cell -> logit -3 (conf 0.047);
     # a modest logit range keeps |w| (and with it the amplification of bf16 feature noise) small
+    if os.environ.get("WT_CALIB_DEBUG"):
+        full = torch.full((n * gh * gw,), -1e9, dtype=torch.float64)
+        full[sel] = torch.where(t == 0, score, torch.tensor(-1e9, dtype=torch.float64))
+        for v, i in zip(*torch.topk(full, 6)):
+            k, r = divmod(int(i), gh * gw)
+            print(f"  neg score {float(v):.3f} view {k} cell (x={r % gw}, y={r // gw}) head cell (x={int(heads[k][0] // 8)}, y={int(heads[k][1] // 8)})")
     alpha = (POS_LOGIT - NEG_LOGIT) / (s_pos - s_neg)
     beta = POS_LOGIT - alpha * s_pos
     w_cls = alpha * w

@@ -46,8 +46,8 @@ __global__ void mse_error_kernel(const double* __restrict__ wrm, const double* _
 
 extern "C" int wt_bbox_error(const double* worm, const double* mic, double* err, int64_t n, void* stream) {
     using namespace wt;
-    WT_REQUIRE(worm && mic && err, "null argument");
     if (n == 0) return 0;
+    WT_REQUIRE(worm && mic && err, "null argument");
     bbox_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(worm, mic, err, n);
     WT_LAUNCHED();
     return 0;
@@ -55,8 +55,8 @@ extern "C" int wt_bbox_error(const double* worm, const double* mic, double* err,
 
 extern "C" int wt_mse_error(const double* worm, const double* mic, double* err, int64_t n, void* stream) {
     using namespace wt;
-    WT_REQUIRE(worm && mic && err, "null argument");
     if (n == 0) return 0;
+    WT_REQUIRE(worm && mic && err, "null argument");
     mse_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(worm, mic, err, n);
     WT_LAUNCHED();
     return 0;

@@ -54,11 +54,11 @@ def worm_track(num_frames: int, seed: int = 0, frame_hw: tuple[int, int] = (FRAM
 
 def render_frame(frame_idx: int, track: np.ndarray, seed: int = 0,
                  frame_hw: tuple[int, int] = (FRAME_H, FRAME_W)) -> np.ndarray:
-    """One (h, w) u8 frame: background 200 +- 6 hash noise; worm = dark capsule (~80 x 8 px) trailing
-    a ~14 px head disc."""
+    """One (h, w) u8 frame: background 200 +- 6 hash noise; worm = tapered body (~80 px long,
+    8 px wide at the head, fading from ~70 to ~140 towards the tail) behind a dark ~14 px head disc (~24)."""
     h, w = frame_hw
     yy, xx = np.meshgrid(np.arange(h, dtype=np.uint32), np.arange(w, dtype=np.uint32), indexing="ij")
-    key = (np.uint32(seed) * np.uint32(0x9E3779B1)) ^ (np.uint32(frame_idx) * np.uint32(0x85EBCA77))
+    key = np.uint32((int(seed) * 0x9E3779B1 ^ int(frame_idx) * 0x85EBCA77) & 0xFFFFFFFF)
     noise = _hash_u32(xx * np.uint32(0x27D4EB2F) ^ yy * np.uint32(0x165667B1) ^ key) % np.uint32(13)
     img = (194 + noise).astype(np.uint8)
 
@@ -73,12 +73,15 @@ def render_frame(frame_idx: int, track: np.ndarray, seed: int = 0,
         u = dx * ca + dy * sa          # along heading (head at u = 0, body trails to u = -80)
         v = -dx * sa + dy * ca
         uc = np.clip(u, -80.0, 0.0)
-        body = (u - uc) ** 2 + v ** 2 <= 4.0 ** 2
+        taper = 1.0 + 0.75 * uc / 80.0                       # 1 at the head .. 0.25 at the tail tip
+        body = (u - uc) ** 2 + v ** 2 <= (4.0 * taper) ** 2
         head = dx ** 2 + dy ** 2 <= 7.0 ** 2
-        mask = body | head
         sub = img[y0:y1, x0:x1]
-        dark = (58 + (noise[y0:y1, x0:x1] % np.uint32(5))).astype(np.uint8)
-        sub[mask] = dark[mask]
+        nz = noise[y0:y1, x0:x1] % np.uint32(5)
+        shade = (68.0 - 70.0 * uc / 80.0).astype(np.uint8) + nz.astype(np.uint8)   # body fades towards the tail
+        sub[body] = shade[body]
+        darker = (22 + nz).astype(np.uint8)                  # the head is the darkest part
+        sub[head] = darker[head]
     return img
 
 
