@@ -21,6 +21,8 @@
 #include "conv.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace wt {
 
 namespace {
@@ -34,7 +36,7 @@ constexpr int kMaxStages = 16;
 
 struct ConvTcParams {
     CUtensorMap tmA[4];   // input views (index = row parity * 2 + col parity for stride 2, else [0])
-    CUtensorMap tmB;      // weights [cout][k*k*cin]
+    CUtensorMap tmB;      // weights [cout][k*k*cin]  (halo kernel: 3-D view [cout][tap][cin])
     CUtensorMap tmD;      // output slice
     CUtensorMap tmR;      // residual slice (bf16)
     const float* bias;
@@ -75,6 +77,138 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Epilogue warps (4 warps, thread e <-> accumulator row e): TMEM -> registers -> bias/SiLU/residual ->
+// swizzled staging smem -> TMA store into the destination channel slice.  Shared by both kernels.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStage, float* sBias,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar,
+                                              uint32_t tmem_base, int warp, int lane) {
+    const int et = threadIdx.x - 64;        // 0..127
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
+    const bool store_thread = (et == 0);
+    // bf16 output: a staging row holds 64 channels (32 when BN == 32); f32 output: 32 channels
+    const int subs_per_unit = p.out_f32 ? 1 : (BN == 32 ? 1 : 2);
+    const int unit_ch = p.out_f32 ? 32 : (BN == 32 ? 32 : 64);
+    const bool rows64 = (!p.out_f32) && (BN == 32);   // 64-byte staging rows (SWIZZLE_64B)
+    const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
+    uint32_t unit_counter = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int nblk = tile % p.n_blocks;
+        int m = tile / p.n_blocks;
+        const int xb = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int yb = m % p.tiles_y;
+        const int nb = m / p.tiles_y;
+        const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
+        const int ab = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+
+        // SiLU path keeps bias/2 so that h = acc * 0.5 + bias/2 is a single FFMA
+        for (int i = et; i < BN; i += kEpiThreads)
+            sBias[i] = __ldg(p.bias + nblk * BN + i) * (p.act == WT_ACT_SILU ? 0.5f : 1.0f);
+
+        ptx::mbar_wait(&tfull_bar[ab], aphase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN;
+
+#pragma unroll 1
+        for (int sub = 0; sub < BN / 32; ++sub) {
+            const int sub_in_unit = sub % subs_per_unit;
+            const int unit = sub / subs_per_unit;
+            const int sb = unit_counter & 1;
+            uint8_t* stage_buf = sStage + sb * kStageBufBytes;
+            if (sub_in_unit == 0) {
+                // the TMA store that last read this staging buffer must have finished reading
+                if (store_thread) ptx::tma_store_wait_read<1>();
+                ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                if (p.has_res && store_thread) {
+                    ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
+                    ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * unit_ch, x0,
+                                     y0, n0);
+                }
+            }
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(t_row + sub * 32, acc);
+            ptx::tmem_ld_wait();
+            float v[32];
+            if (p.act == WT_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float h = fmaf(__uint_as_float(acc[j]), 0.5f, sBias[sub * 32 + j]);
+                    v[j] = fmaf(h, tanh_fast(h), h);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
+            }
+            if (p.has_res && sub_in_unit == 0) ptx::mbar_wait(&res_bar[sb], (unit_counter >> 1) & 1);
+
+            if (p.out_f32) {
+                // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B
+                uint8_t* rowp = stage_buf + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = o;
+                }
+            } else {
+                // 32 bf16 = 64 B = 4 chunks of 16 B
+                uint8_t* rowp;
+                int cbase, xr;
+                if (rows64) {
+                    rowp = stage_buf + row * 64;
+                    cbase = 0;
+                    xr = (row >> 1) & 3;
+                } else {
+                    rowp = stage_buf + row * 128;
+                    cbase = sub_in_unit * 4;
+                    xr = row & 7;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4* dstp = reinterpret_cast<uint4*>(rowp + (((cbase + c) ^ xr) << 4));
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = v[8 * c + j];
+                    if (p.has_res) {
+                        const uint4 r = *dstp;
+                        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[2 * j] += __uint_as_float(rw[j] << 16);
+                            f[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+                        }
+                    }
+                    uint4 o;
+                    o.x = pack_bf16(f[0], f[1]);
+                    o.y = pack_bf16(f[2], f[3]);
+                    o.z = pack_bf16(f[4], f[5]);
+                    o.w = pack_bf16(f[6], f[7]);
+                    *dstp = o;
+                }
+            }
+            if (sub == BN / 32 - 1) {
+                // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[ab]);
+            }
+            if (sub_in_unit == subs_per_unit - 1) {
+                ptx::fence_proxy_async_smem();
+                ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                if (store_thread) {
+                    ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * unit_ch, x0, y0, n0);
+                    ptx::tma_store_commit();
+                }
+                ++unit_counter;
+            }
+        }
+    }
+    if (store_thread) ptx::tma_store_wait<0>();
+}
+
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     using L = SmemLayout<BN, BK>;
@@ -97,7 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* res_bar = bars + 2 * kStages + 4;      // [2]       residual TMA -> epilogue
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
 
-    const int warp = threadIdx.x >> 5;
+    // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
+    // and the producer / MMA loops can live on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -131,90 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nblk = tile % p.n_blocks;
-                int m = tile / p.n_blocks;
-                const int xb = m % p.tiles_x;
-                m /= p.tiles_x;
-                const int yb = m % p.tiles_y;
-                const int nb = m / p.tiles_y;
-                const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
-                for (int tap = 0; tap < taps; ++tap) {
-                    const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                    int ax, ay, mapi;
-                    if (p.stride == 1) {
-                        ax = x0 + kw - pad;
-                        ay = y0 + kh - pad;
-                        mapi = 0;
-                    } else {   // stride 2, 3x3, pad 1: input row 2*oy+kh-1 -> parity view + offset
-                        ax = x0 + (kw == 0 ? -1 : 0);
-                        ay = y0 + (kh == 0 ? -1 : 0);
-                        mapi = ((kh != 1) ? 2 : 0) + ((kw != 1) ? 1 : 0);
-                    }
-                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                        ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
-                                         p.src_coff + cb * BK, ax, ay, n0);
-                        ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
-                                         nblk * BN);
-                        if (++stage == kStages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const int ab = it & 1;
-                const uint32_t aphase = (it >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);   // epilogue has drained this accumulator
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + ab * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sA + stage * L::kABytes));
-                    const uint64_t b_desc = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB + stage * L::kBBytes));
-#pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        // advance 16 bf16 = 32 B along K inside the swizzle span: start address += 2
-                        ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0);
-                    }
-                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs finish
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-                ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int et = threadIdx.x - 64;        // 0..127
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
-        const bool store_thread = (et == 0);
-        // bf16 output: a staging row holds 64 channels (32 when BN == 32); f32 output: 32 channels
-        const int subs_per_unit = p.out_f32 ? 1 : (BN == 32 ? 1 : 2);
-        const int unit_ch = p.out_f32 ? 32 : (BN == 32 ? 32 : 64);
-        const bool rows64 = (!p.out_f32) && (BN == 32);   // 64-byte staging rows (SWIZZLE_64B)
-        const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
-        uint32_t unit_counter = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        // The whole warp walks the loop (uniform control flow); one elected lane issues the copies.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int nblk = tile % p.n_blocks;
             int m = tile / p.n_blocks;
             const int xb = m % p.tiles_x;
@@ -222,111 +278,239 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int yb = m % p.tiles_y;
             const int nb = m / p.tiles_y;
             const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
-            const int ab = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-
-            // SiLU path keeps bias/2 so that h = acc * 0.5 + bias/2 is a single FFMA
-            for (int i = et; i < BN; i += kEpiThreads)
-                sBias[i] = __ldg(p.bias + nblk * BN + i) * (p.act == WT_ACT_SILU ? 0.5f : 1.0f);
-
-            ptx::mbar_wait(&tfull_bar[ab], aphase);
-            ptx::tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN;
-
-#pragma unroll 1
-            for (int sub = 0; sub < BN / 32; ++sub) {
-                const int sub_in_unit = sub % subs_per_unit;
-                const int unit = sub / subs_per_unit;
-                const int sb = unit_counter & 1;
-                uint8_t* stage_buf = sStage + sb * kStageBufBytes;
-                if (sub_in_unit == 0) {
-                    // the TMA store that last read this staging buffer must have finished reading
-                    if (store_thread) ptx::tma_store_wait_read<1>();
-                    ptx::bar_sync(kEpiBarrier, kEpiThreads);
-                    if (p.has_res && store_thread) {
-                        ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
-                        ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * unit_ch, x0,
-                                         y0, n0);
-                    }
+            for (int tap = 0; tap < taps; ++tap) {
+                const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                int ax, ay, mapi;
+                if (p.stride == 1) {
+                    ax = x0 + kw - pad;
+                    ay = y0 + kh - pad;
+                    mapi = 0;
+                } else {   // stride 2, 3x3, pad 1: input row 2*oy+kh-1 -> parity view + offset
+                    ax = x0 + (kw == 0 ? -1 : 0);
+                    ay = y0 + (kh == 0 ? -1 : 0);
+                    mapi = ((kh != 1) ? 2 : 0) + ((kw != 1) ? 1 : 0);
                 }
-                uint32_t acc[32];
-                ptx::tmem_ld_32x32(t_row + sub * 32, acc);
-                ptx::tmem_ld_wait();
-                float v[32];
-                if (p.act == WT_ACT_SILU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float h = fmaf(__uint_as_float(acc[j]), 0.5f, sBias[sub * 32 + j]);
-                        v[j] = fmaf(h, tanh_fast(h), h);
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                        ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                         p.src_coff + cb * BK, ax, ay, n0);
+                        ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
+                                         nblk * BN);
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
-                }
-                if (p.has_res && sub_in_unit == 0) ptx::mbar_wait(&res_bar[sb], (unit_counter >> 1) & 1);
-
-                if (p.out_f32) {
-                    // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B
-                    uint8_t* rowp = stage_buf + row * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                        *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = o;
-                    }
-                } else {
-                    // 32 bf16 = 64 B = 4 chunks of 16 B
-                    uint8_t* rowp;
-                    int cbase, xr;
-                    if (rows64) {
-                        rowp = stage_buf + row * 64;
-                        cbase = 0;
-                        xr = (row >> 1) & 3;
-                    } else {
-                        rowp = stage_buf + row * 128;
-                        cbase = sub_in_unit * 4;
-                        xr = row & 7;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4* dstp = reinterpret_cast<uint4*>(rowp + (((cbase + c) ^ xr) << 4));
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = v[8 * c + j];
-                        if (p.has_res) {
-                            const uint4 r = *dstp;
-                            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[2 * j] += __uint_as_float(rw[j] << 16);
-                                f[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
-                            }
-                        }
-                        uint4 o;
-                        o.x = pack_bf16(f[0], f[1]);
-                        o.y = pack_bf16(f[2], f[3]);
-                        o.z = pack_bf16(f[4], f[5]);
-                        o.w = pack_bf16(f[6], f[7]);
-                        *dstp = o;
-                    }
-                }
-                if (sub == BN / 32 - 1) {
-                    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-                    ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[ab]);
-                }
-                if (sub_in_unit == subs_per_unit - 1) {
-                    ptx::fence_proxy_async_smem();
-                    ptx::bar_sync(kEpiBarrier, kEpiThreads);
-                    if (store_thread) {
-                        ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * unit_ch, x0, y0, n0);
-                        ptx::tma_store_commit();
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
                     }
-                    ++unit_counter;
                 }
             }
         }
-        if (store_thread) ptx::tma_store_wait<0>();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        // Warp-uniform loop; one elected lane issues the UMMAs and the commits.
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+        const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);   // epilogue has drained this accumulator
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + ab * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint64_t a_desc = ptx::make_kmajor_desc<kRowBytes>(sA_u32 + stage * L::kABytes);
+                    const uint64_t b_desc = ptx::make_kmajor_desc<kRowBytes>(sB_u32 + stage * L::kBBytes);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle span: start address += 2
+                        ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs finish
+                    if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 / stride-1 variant with shared-memory halo reuse.
+//
+// The generic kernel above re-reads the input once per filter tap (9 TMA boxes per channel block),
+// which makes the 3x3 layers L2-bandwidth bound.  Here the tile is 16 rows x 8 columns of one image
+// and the producer loads the (16+2) x (8+2) halo of a 64-channel block ONCE; the nine taps are nine
+// UMMA descriptors into that buffer: tap (kh, kw) starts (kh*10 + kw) pixels in, the 8 pixels of a
+// tile row are 8 consecutive 128-byte rows (one swizzle group) and consecutive tile rows are one
+// halo row (10 pixels = 1280 B) apart, which is the descriptor's stride-byte-offset.  The 128-byte
+// swizzle is a function of the shared-memory address (verified on B200: no descriptor base offset
+// is needed), so TMA (writer) and UMMA (reader) agree on it for any start pixel.  Layers with 32
+// input channels use the same 64-wide K block: the tensor maps end at the slice's last channel, so
+// TMA zero-fills the upper half of both operands.  Weights stream through their own, deeper pipeline (one BN x 64 tile per tap).
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloABytes = ((kHaloW * kHaloH * 128 + 1023) / 1024) * 1024;   // 23552
+
+template <int BN>
+struct HaloSmem {
+    static constexpr int kAStages = 3;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 1024;
+    static constexpr int kBudget = 232448 - 1024;
+    static constexpr int kBStagesRaw = (kBudget - kFixedBytes - kAStages * kHaloABytes) / kBBytes;
+    static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
+    static constexpr int kTotalBytes = kAStages * kHaloABytes + kBStages * kBBytes + kFixedBytes + 1024;
+    static_assert(kBStages >= 3, "not enough shared memory for the weight pipeline");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
+    using L = HaloSmem<BN>;
+    constexpr int kAStages = L::kAStages, kBStages = L::kBStages;
+    constexpr uint32_t kTmemCols = 2 * BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                        // [kAStages] halo tiles (180 px x 128 B, swizzled)
+    uint8_t* sB = smem + kAStages * kHaloABytes;               // [kBStages][BN][64] bf16
+    uint8_t* sStage = sB + kBStages * L::kBBytes;
+    float* sBias = reinterpret_cast<float*>(sStage + 2 * kStageBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint64_t* afull = bars;
+    uint64_t* aempty = afull + kAStages;
+    uint64_t* bfull = aempty + kAStages;
+    uint64_t* bempty = bfull + kBStages;
+    uint64_t* tfull_bar = bempty + kBStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* res_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+
+    // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
+    // and the producer / MMA loops can live on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.tmA[0]);
+        ptx::prefetch_tmap(&p.tmB);
+        ptx::prefetch_tmap(&p.tmD);
+        if (p.has_res) ptx::prefetch_tmap(&p.tmR);
+        for (int s = 0; s < kAStages; ++s) {
+            ptx::mbar_init(&afull[s], 1);
+            ptx::mbar_init(&aempty[s], 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            ptx::mbar_init(&bfull[s], 1);
+            ptx::mbar_init(&bempty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&res_bar[i], 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // TMA producer: warp-uniform loop, one elected lane issues
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nblk = tile % p.n_blocks;
+            int m = tile / p.n_blocks;
+            const int xb = m % p.tiles_x;
+            m /= p.tiles_x;
+            const int yb = m % p.tiles_y;
+            const int nb = m / p.tiles_y;
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                ptx::mbar_wait(&aempty[sa], pa ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * 128);
+                    ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * 64, xb * 8 - 1,
+                                     yb * 16 - 1, nb);
+                }
+                __syncwarp();
+                if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    ptx::mbar_wait(&bempty[sb], pb ^ 1);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
+                        ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * 64, tap, nblk * BN);
+                    }
+                    __syncwarp();
+                    if (++sb == kBStages) { sb = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+        const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + ab * BN;
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                ptx::mbar_wait(&afull[sa], pa);
+                const uint32_t a_base = sA_u32 + sa * kHaloABytes;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    ptx::mbar_wait(&bfull[sb], pb);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const uint64_t a_desc = ptx::make_kmajor_desc_sbo(a_base + (kh * kHaloW + kw) * 128, kHaloW * 128);
+                        const uint64_t b_desc = ptx::make_kmajor_desc<128>(sB_u32 + sb * L::kBBytes);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (cb | tap | kk) != 0);
+                        ptx::umma_commit(&bempty[sb]);
+                        if (tap == 8) {
+                            ptx::umma_commit(&aempty[sa]);
+                            if (cb == p.cin_blocks - 1) ptx::umma_commit(&tfull_bar[ab]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++sb == kBStages) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == kAStages) { sa = 0; pa ^= 1; }
+            }
+        }
+    } else {
+        conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
     }
 
     ptx::tc_fence_before();
@@ -343,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 struct ConvTcPlan {
     ConvTcParams prm;
+    bool halo;
     int bn, bk;
     int pix_per_image_tiles;   // tiles_x * tiles_y
 };
@@ -380,7 +565,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     WT_REQUIRE(d.dst.dtype == WT_DT_BF16 || d.dst.dtype == WT_DT_F32, "conv output must be bf16 or f32");
     const int bn = pick_bn(d.cout);
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
-    const int bk = (d.cin % 64 == 0) ? 64 : 32;
+    int bk = (d.cin % 64 == 0) ? 64 : 32;
     WT_REQUIRE(d.cin % bk == 0, "cin must be a multiple of 32");
     const int ho = d.dst.h, wo = d.dst.w;
     if (d.stride == 1) {
@@ -398,7 +583,20 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     ConvTcParams& p = pl->prm;
     pl->bn = bn;
     pl->bk = bk;
-    choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
+    // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
+    // map height wastes more than a quarter of the 16-row tiles (20x20 maps stay on the generic kernel)
+    static const int halo_env = getenv("WT_CONV_HALO") ? atoi(getenv("WT_CONV_HALO")) : 1;
+    pl->halo = halo_env != 0 && d.k == 3 && d.stride == 1 && (d.cin % 64 == 0 || d.cin == 32) && wo % 8 == 0 &&
+               ceil_div(ho, 16) * 16 * 4 <= ho * 5;
+    if (pl->halo) {
+        bk = 64;
+        pl->bk = 64;
+        p.tw = 8;
+        p.th = 16;
+        p.tn = 1;
+    } else {
+        choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
+    }
     p.tiles_x = ceil_div(wo, p.tw);
     p.tiles_y = ceil_div(ho, p.th);
     p.tiles_n = ceil_div(d.batch, p.tn);
@@ -406,7 +604,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.ksize = d.k;
     p.stride = d.stride;
     p.cin = d.cin;
-    p.cin_blocks = d.cin / bk;
+    p.cin_blocks = ceil_div(d.cin, bk);
     p.src_coff = d.src.coff;
     p.dst_coff = d.dst.coff;
     p.res_coff = d.res.base ? d.res.coff : 0;
@@ -419,9 +617,11 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
 
     const int sw_in = bk * 2;   // swizzle span == K-block row bytes
     int rc = 0;
-    const uint32_t box_a[4] = {uint32_t(bk), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+    const uint32_t box_a[4] = {uint32_t(bk), uint32_t(pl->halo ? kHaloW : p.tw), uint32_t(pl->halo ? kHaloH : p.th),
+                               uint32_t(p.tn)};
     if (d.stride == 1) {
-        const uint64_t dims[4] = {uint64_t(d.src.ctot), uint64_t(d.src.w), uint64_t(d.src.h), uint64_t(d.batch)};
+        // the channel extent ends with the slice, so a K block wider than the slice is zero-filled
+        const uint64_t dims[4] = {uint64_t(d.src.coff + d.cin), uint64_t(d.src.w), uint64_t(d.src.h), uint64_t(d.batch)};
         const uint64_t str[3] = {uint64_t(d.src.ctot) * 2, uint64_t(d.src.ctot) * 2 * d.src.w,
                                  uint64_t(d.src.ctot) * 2 * d.src.w * d.src.h};
         rc |= encode_tmap(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.src.base, dims, str, box_a, sw_in);
@@ -438,7 +638,13 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
                                   sw_in);
             }
     }
-    {
+    if (pl->halo) {
+        const uint64_t dims[3] = {uint64_t(d.cin), 9, uint64_t(d.cout)};
+        const uint64_t str[2] = {uint64_t(d.cin) * 2, uint64_t(d.cin) * 2 * 9};
+        const uint32_t box[3] = {64, 1, uint32_t(bn)};
+        rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
+                          128);
+    } else {
         const uint64_t ktot = uint64_t(d.k) * d.k * d.cin;
         const uint64_t dims[2] = {ktot, uint64_t(d.cout)};
         const uint64_t str[1] = {ktot * 2};
@@ -494,12 +700,34 @@ static int launch_inst(const ConvTcParams& prm, int grid, cudaStream_t stream) {
     return 0;
 }
 
+template <int BN>
+static int launch_halo(const ConvTcParams& prm, int grid, cudaStream_t stream) {
+    using L = HaloSmem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           L::kTotalBytes));
+        configured = true;
+    }
+    conv_halo_kernel<BN><<<grid, kThreads, L::kTotalBytes, stream>>>(prm);
+    WT_LAUNCHED();
+    return 0;
+}
+
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
     ConvTcParams prm = pl->prm;
     const int tiles_n = ceil_div(n_images, prm.tn);
     prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;
     if (prm.num_tiles == 0) return 0;
     const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+    if (pl->halo) {
+        switch (pl->bn) {
+            case 256: return launch_halo<256>(prm, grid, stream);
+            case 128: return launch_halo<128>(prm, grid, stream);
+            case 64:  return launch_halo<64>(prm, grid, stream);
+            case 32:  return launch_halo<32>(prm, grid, stream);
+        }
+    }
     const int key = pl->bn * 100 + pl->bk;
     switch (key) {
         case 25664: return launch_inst<256, 64>(prm, grid, stream);

@@ -51,47 +51,64 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, 
 }
 
 // ------------------------------------------------------------------ first layer
-// One thread per output pixel; weights (grey-folded, /255 folded) broadcast from shared memory.
+// u8 grey -> COUT channels, 3x3 stride 2 pad 1, fp32 math.  One thread = 4 horizontally adjacent
+// output pixels x 8 output channels: the 72 weights of its channel group stay in registers (no
+// shared-memory traffic in the FMA loop), the 3 x 9 input bytes are read once, and the four lanes
+// of a pixel quad together store 64 contiguous bytes per pixel.
 template <int COUT>
 __global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
                                                     const float* __restrict__ w9, const float* __restrict__ bias,
                                                     int act, __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
-                                                    long long total) {
-    __shared__ float sw[COUT * 9];
-    __shared__ float sb[COUT];
-    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) sw[i] = w9[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
-    __syncthreads();
+                                                    long long total_threads) {
+    constexpr int G = COUT / 8;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int ho = h / 2, wo = w / 2;
-    const int x = int(idx % wo);
-    const int y = int((idx / wo) % ho);
-    const int n = int(idx / (long long)(wo * ho));
+    if (idx >= total_threads) return;
+    const int g = int(idx % G);
+    long long q = idx / G;
+    const int ho = h / 2, wo = w / 2, qw = wo / 4;
+    const int xq = int(q % qw);
+    q /= qw;
+    const int y = int(q % ho);
+    const int n = int(q / ho);
+    const int x0 = xq * 4;
+
+    float wreg[9][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wreg[t][j] = __ldg(w9 + (g * 8 + j) * 9 + t);
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float b = __ldg(bias + g * 8 + j);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][j] = b;
+    }
     const uint8_t* img = src + size_t(n) * h * w;
-    float in[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
         const int iy = 2 * y + kh - 1;
+        const bool row_ok = iy >= 0 && iy < h;
+        const uint8_t* rowp = img + size_t(row_ok ? iy : 0) * w;
+        float in[9];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int ix = 2 * x + kw - 1;
-            const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
-            in[kh * 3 + kw] = ok ? float(__ldg(img + size_t(iy) * w + ix)) : 0.f;
+        for (int c = 0; c < 9; ++c) {
+            const int ix = 2 * x0 - 1 + c;
+            in[c] = (row_ok && ix >= 0 && ix < w) ? float(__ldg(rowp + ix)) : 0.f;
         }
-    }
-    __nv_bfloat16* out = dst + size_t(idx) * dct + dcoff;
 #pragma unroll
-    for (int g = 0; g < COUT / 8; ++g) {
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[2 * p + kw], wreg[kh * 3 + kw][j], acc[p][j]);
+    }
+    __nv_bfloat16* out = dst + ((size_t(n) * ho + y) * wo + x0) * dct + dcoff + g * 8;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float* wp = sw + (g * 8 + j) * 9;
-            float a = sb[g * 8 + j];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(in[t], wp[t], a);
-            o[j] = act == WT_ACT_SILU ? silu_f(a) : a;
-        }
+        for (int j = 0; j < 8; ++j) o[j] = act == WT_ACT_SILU ? silu_f(acc[p][j]) : acc[p][j];
         uint4 pk;
         __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
         __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
@@ -101,7 +118,7 @@ __global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ 
         pk.y = *reinterpret_cast<uint32_t*>(&t1);
         pk.z = *reinterpret_cast<uint32_t*>(&t2);
         pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(out + g * 8) = pk;
+        *reinterpret_cast<uint4*>(out + size_t(p) * dct) = pk;
     }
 }
 
@@ -190,10 +207,10 @@ int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream) {
 int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float* bias, int cout, int act,
                  const TensorView& dst, int n_images, cudaStream_t stream) {
     WT_REQUIRE(cout == 32 || cout == 16 || cout == 64, "conv0 supports 16/32/64 output channels");
-    WT_REQUIRE(h % 2 == 0 && w % 2 == 0, "conv0 needs an even input size");
+    WT_REQUIRE(h % 2 == 0 && w % 8 == 0, "conv0 needs an even height and a width that is a multiple of 8");
     WT_REQUIRE(dst.dtype == WT_DT_BF16 && dst.h == h / 2 && dst.w == w / 2, "conv0 destination shape");
     WT_REQUIRE(dst.ctot % 8 == 0 && dst.coff % 8 == 0, "conv0 destination channel alignment");
-    const long long total = (long long)n_images * (h / 2) * (w / 2);
+    const long long total = (long long)n_images * (h / 2) * (w / 8) * (cout / 8);   // pixel quads x channel groups
     if (total == 0) return 0;
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);

@@ -29,6 +29,7 @@ struct PostParams {
     wt_post_params pp;
     float* out_boxes;
     int32_t* out_count;
+    float* sc_logit;     // [n][A] class logits computed from cls_feat
     float* sc_box;       // [n][A][4] candidate boxes in sorted order (xyxy, letterboxed px)
     float* sc_conf;      // [n][A]
     int32_t* sc_idx;     // [n][A]
@@ -112,9 +113,43 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
     return ovr > thr;
 }
 
+// Class logit of every anchor: the final 1x1 convolution of the cls branch (cout = nc = 1) as a dot
+// product, 16 lanes per anchor (one 16-byte chunk of the bf16 feature vector each), fp32.
+__global__ void __launch_bounds__(256) cls_logit_kernel(const PostParams p, int n) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long ag = t >> 4;
+    const int sub = int(t & 15);
+    const bool live = ag < (long long)n * p.total_anchors;
+    float acc = 0.f;
+    int img = 0, a = 0, l = 0;
+    if (live) {
+        img = int(ag / p.total_anchors);
+        a = int(ag - (long long)img * p.total_anchors);
+        l = level_of(p, a);
+        const wt_head_level& L = p.lv[l];
+        if (L.cls_feat) {
+            const int local = a - p.level_start[l];
+            const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(L.cls_feat) + (size_t(img) * L.h * L.w + local) * L.cls_c;
+            const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(L.cls_w);
+            for (int c = sub * 8; c < L.cls_c; c += 128) {
+                const uint4 fv = __ldg(reinterpret_cast<const uint4*>(f + c));
+                const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + c));
+                const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc = fmaf(bf16_lo(fw[j]), bf16_lo(ww[j]), acc);
+                    acc = fmaf(bf16_hi(fw[j]), bf16_hi(ww[j]), acc);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && sub == 0 && p.lv[l].cls_feat) p.sc_logit[size_t(img) * p.total_anchors + a] = acc + p.lv[l].cls_b;
+}
+
 __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) {
     extern __shared__ unsigned long long keys[];            // [sort_cap]
-    __shared__ float s_clsw[kMaxLevels * kMaxClsC / 4];      // fp32 copy of the cls weights (<= 4 x 256) — see host check
     __shared__ int s_count;
     __shared__ unsigned long long s_red[kPostThreads / 32];
     __shared__ float4 s_keep[kMaxKeep];
@@ -126,40 +161,16 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     const int A = p.total_anchors;
 
     if (tid == 0) { s_count = 0; s_nkeep = 0; }
-    for (int l = 0; l < p.n_levels; ++l) {
-        if (p.lv[l].cls_feat) {
-            const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.lv[l].cls_w);
-            for (int c = tid; c < p.lv[l].cls_c; c += kPostThreads) s_clsw[l * (kMaxClsC / 4) + c] = __bfloat162float(w[c]);
-        }
-    }
     __syncthreads();
 
-    // ---- (a) confidence + filter
-    for (int a = warp; a < A; a += kPostThreads / 32) {
+    // ---- (a) confidence + filter (logits are ready: either given or computed by cls_logit_kernel)
+    for (int a = tid; a < A; a += kPostThreads) {
         const int l = level_of(p, a);
         const wt_head_level& L = p.lv[l];
-        const int local = a - p.level_start[l];
-        const size_t pix = size_t(img) * L.h * L.w + local;
-        float logit;
-        if (L.cls_logit) {
-            logit = __ldg(L.cls_logit + pix);
-        } else {
-            const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(L.cls_feat) + pix * L.cls_c;
-            const float* w = s_clsw + l * (kMaxClsC / 4);
-            float acc = 0.f;
-            for (int c = lane * 4; c < L.cls_c; c += 128) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(f + c));
-                acc = fmaf(bf16_lo(v.x), w[c], acc);
-                acc = fmaf(bf16_hi(v.x), w[c + 1], acc);
-                acc = fmaf(bf16_lo(v.y), w[c + 2], acc);
-                acc = fmaf(bf16_hi(v.y), w[c + 3], acc);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            logit = acc + L.cls_b;
-        }
+        const float logit = L.cls_logit ? __ldg(L.cls_logit + size_t(img) * L.h * L.w + (a - p.level_start[l]))
+                                        : p.sc_logit[size_t(img) * A + a];
         const float conf = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
-        if (lane == 0 && conf > p.pp.conf_thres) {
+        if (conf > p.pp.conf_thres) {
             const int pos = atomicAdd(&s_count, 1);
             keys[pos] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - unsigned(a));
         }
@@ -305,7 +316,7 @@ extern "C" int wt_track_rows(const float* boxes, const int32_t* count, int max_d
 }
 
 extern "C" int64_t wt_post_scratch_bytes(int n, int total_anchors) {
-    return int64_t(n) * total_anchors * (4 * 4 + 4 + 4) + 256;
+    return int64_t(n) * total_anchors * (4 * 4 + 4 + 4 + 4) + 256;
 }
 
 extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* pp,
@@ -323,7 +334,7 @@ extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, c
         WT_REQUIRE(levels[l].box, "box logits missing");
         WT_REQUIRE((levels[l].cls_feat != nullptr) != (levels[l].cls_logit != nullptr), "give cls_feat or cls_logit");
         if (levels[l].cls_feat)
-            WT_REQUIRE(levels[l].cls_c % 4 == 0 && levels[l].cls_c <= kMaxClsC / 4 && levels[l].cls_w, "cls feature channels");
+            WT_REQUIRE(levels[l].cls_c % 8 == 0 && levels[l].cls_c <= kMaxClsC && levels[l].cls_w, "cls feature channels");
     }
     for (int l = n_levels; l <= kMaxLevels; ++l) p.level_start[l] = total;
     p.n_levels = n_levels;
@@ -340,11 +351,19 @@ extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, c
     p.sc_box = reinterpret_cast<float*>(sc);
     p.sc_conf = reinterpret_cast<float*>(sc + size_t(n) * total * 16);
     p.sc_idx = reinterpret_cast<int32_t*>(sc + size_t(n) * total * 20);
+    p.sc_logit = reinterpret_cast<float*>(sc + size_t(n) * total * 24);
     if (n == 0) return 0;
     static size_t configured = 0;
     if (smem > configured) {
         WT_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
+    }
+    bool any_feat = false;
+    for (int l = 0; l < n_levels; ++l) any_feat |= levels[l].cls_feat != nullptr;
+    if (any_feat) {
+        const long long threads = (long long)n * total * 16;
+        cls_logit_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n);
+        WT_LAUNCHED();
     }
     post_kernel<<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     WT_LAUNCHED();

@@ -50,9 +50,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// The spin lives inside one asm statement so that the compiler sees straight-line, warp-uniform code
+// around it (a C++ loop on the per-thread predicate would make everything after it "divergent" and
+// force every later uniform-datapath instruction — UTCHMMA, UTMALDG — through an election loop).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+        "@P bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -63,6 +75,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, ui
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -157,6 +175,16 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     d |= sbo << 32;                                          // stride byte offset, bits [32,46)
     d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (Blackwell)
     d |= layout << 61;                                       // swizzle mode, bits [61,64)
+    return d;
+}
+// Same, 128-byte rows / SWIZZLE_128B, with an explicit stride between 8-row groups (halo tiles).
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, dense.
