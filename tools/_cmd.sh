@@ -1,6 +1,4 @@
 export PYTHONPATH=$PWD
-python tools/gpu_detector_check.py 640 640 2>&1 | grep -E "^x|^m[0-9]|head|oracle" | head -40 > gpurun_out/det_exact.log
-WT_SILU_TANH=1 python tools/gpu_detector_check.py 640 640 2>&1 | grep -E "^x|^m[0-9]|head|oracle" | head -40 > gpurun_out/det_tanh.log
-python tools/gpu_layer_times.py 64 640 > gpurun_out/layers_exact.log 2>&1; head -1 gpurun_out/layers_exact.log
-WT_SILU_TANH=1 python tools/gpu_layer_times.py 64 640 > gpurun_out/layers_tanh.log 2>&1; head -1 gpurun_out/layers_tanh.log
-python -m pytest tests -m gpu -q 2>&1 | tail -3
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_r1c.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'conv0|cls_logit|resmlp|post_kernel|pre_kernel|upsample|sppf' -s 24 -c 8 -o gpurun_out/misc_r1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_misc_r1.log 2>&1
+tail -2 gpurun_out/ncu_misc_r1.log | cut -c1-300

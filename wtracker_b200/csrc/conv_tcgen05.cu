@@ -14,9 +14,10 @@
 // K-major descriptor expects.  Stride-2 convs use four parity views of the input (even/odd rows x
 // even/odd columns), so each tap is again a dense box.
 //
-// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer and
-// TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  The TMEM
-// accumulator is double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer and
+// TMEM owner, warps 2..5 / 6..9 = two epilogue groups (TMEM -> registers -> swizzled smem -> TMA
+// store).  The TMEM accumulator is double-buffered and each epilogue group owns one buffer, so the
+// epilogues of tiles i and i+1 overlap each other and the main loop of tile i+2.
 #include "../../include/wtracker_b200.h"
 #include "conv.cuh"
 #include "ptx.cuh"
@@ -28,10 +29,14 @@ namespace wt {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
-constexpr int kEpiBarrier = 1;          // named barrier id for the 4 epilogue warps
+constexpr int kEpiGroups = 2;           // epilogue warp groups; group g drains TMEM accumulator g (tiles it % 2 == g)
+constexpr int kEpiThreads = 128;        // threads per epilogue group (4 warps = the 4 TMEM lane quadrants)
+constexpr int kThreads = 64 + kEpiGroups * kEpiThreads;
+constexpr int kEpiBarrier = 1;          // named barrier ids kEpiBarrier + group
 constexpr int kStageBufBytes = 16384;   // one epilogue staging buffer: 128 rows x 128 B
+constexpr int kSmemBudget = 232448;   // 227 KB opt-in maximum per CTA
+constexpr int kBarrierBytes = 512;
+constexpr int kMaxCout = 512;           // bias vector kept in shared memory
 constexpr int kMaxStages = 16;
 
 struct ConvTcParams {
@@ -45,9 +50,16 @@ struct ConvTcParams {
     int tw, th, tn;                  // pixel patch, tw*th*tn == 128
     int ksize, stride;
     int cin, cin_blocks;             // cin / BK
+    int cout;
     int src_coff, dst_coff, res_coff;
     int act, has_res, out_f32;
     int num_tiles;
+    // shared-memory plan (host-chosen): pipeline depth and epilogue staging buffers per group (1 | 2).
+    // HBM-bound layers (1x1, narrow N) want two staging buffers per epilogue group, MMA-bound layers
+    // want the bytes as pipeline stages instead.
+    int stages;        // generic kernel: A+B stages; halo kernel: weight (B) stages
+    int a_stages;      // halo kernel: halo-tile stages
+    int epi_bufs;
 };
 
 template <int BN, int BK>
@@ -56,13 +68,12 @@ struct SmemLayout {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = BN * kRowBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 1024;  // staging + bias + barriers
-    static constexpr int kBudget = 232448 - 1024;                          // 227 KB minus alignment slack
-    static constexpr int kStagesRaw = (kBudget - kFixedBytes) / kStageBytes;
-    static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
-    static constexpr int kTotalBytes = kStages * kStageBytes + kFixedBytes + 1024;
-    static_assert(kStages >= 2, "not enough shared memory for a pipeline");
 };
+
+// bytes after the pipeline stages: epilogue staging + bias vector + barriers
+__host__ __device__ constexpr int fixed_smem_bytes(int epi_bufs) {
+    return kEpiGroups * epi_bufs * kStageBufBytes + kMaxCout * 4 + kBarrierBytes;
+}
 
 // SiLU(v) = v * sigmoid(v) = h * tanh(h) + h with h = v / 2: ONE MUFU op (tanh.approx) per element
 // instead of two (ex2 + rcp) — the epilogue warps are MUFU/issue bound, not the tensor pipe.  Measured on
@@ -81,24 +92,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Epilogue warps (4 warps, thread e <-> accumulator row e): TMEM -> registers -> bias/SiLU/residual ->
-// swizzled staging smem -> TMA store into the destination channel slice.  Shared by both kernels.
+// Epilogue: two groups of 4 warps; group g owns TMEM accumulator g and therefore every second tile of
+// this CTA, so the latency chain of one tile (TMEM load -> bias/SiLU/residual -> swizzled staging smem
+// -> TMA store) overlaps the chain of the next tile as well as the MMA main loop.  Thread e of a group
+// <-> accumulator row e (pixel e of the tile).  sBias holds the layer's whole bias vector.
 template <int BN>
-__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStage, float* sBias,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar,
+__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
                                               uint32_t tmem_base, int warp, int lane) {
-    const int et = threadIdx.x - 64;        // 0..127
+    const int g = (warp - 2) >> 2;          // epilogue group == accumulator buffer
+    const int et = threadIdx.x - 64 - g * kEpiThreads;   // 0..127 inside the group
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
     const bool store_thread = (et == 0);
+    const bool two_bufs = p.epi_bufs == 2;
+    uint8_t* sStage = sStageAll + g * p.epi_bufs * kStageBufBytes;
+    uint64_t* res_bar = res_bar_all + 2 * g;
+    const int bar_id = kEpiBarrier + g;
     // bf16 output: a staging row holds 64 channels (32 when BN == 32); f32 output: 32 channels
     const int subs_per_unit = p.out_f32 ? 1 : (BN == 32 ? 1 : 2);
     const int unit_ch = p.out_f32 ? 32 : (BN == 32 ? 32 : 64);
     const bool rows64 = (!p.out_f32) && (BN == 32);   // 64-byte staging rows (SWIZZLE_64B)
     const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
     uint32_t unit_counter = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
         const int nblk = tile % p.n_blocks;
         int m = tile / p.n_blocks;
         const int xb = m % p.tiles_x;
@@ -106,55 +124,61 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
         const int yb = m % p.tiles_y;
         const int nb = m / p.tiles_y;
         const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
-        const int ab = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const float* bias = sBias + nblk * BN;
 
-        // tanh-SiLU path keeps bias/2 so that h = acc * 0.5 + bias/2 is a single FFMA
-        for (int i = et; i < BN; i += kEpiThreads)
-            sBias[i] = __ldg(p.bias + nblk * BN + i) * (p.act == kActSiluTanh ? 0.5f : 1.0f);
-
-        ptx::mbar_wait(&tfull_bar[ab], aphase);
+        ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ab * BN;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
 
 #pragma unroll 1
         for (int sub = 0; sub < BN / 32; ++sub) {
             const int sub_in_unit = sub % subs_per_unit;
             const int unit = sub / subs_per_unit;
-            const int sb = unit_counter & 1;
+            const int sb = two_bufs ? (unit_counter & 1) : 0;
             uint8_t* stage_buf = sStage + sb * kStageBufBytes;
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(t_row + sub * 32, acc);
             if (sub_in_unit == 0) {
                 // the TMA store that last read this staging buffer must have finished reading
-                if (store_thread) ptx::tma_store_wait_read<1>();
-                ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                if (store_thread) {
+                    if (two_bufs) ptx::tma_store_wait_read<1>();
+                    else ptx::tma_store_wait_read<0>();
+                }
+                ptx::bar_sync(bar_id, kEpiThreads);
                 if (p.has_res && store_thread) {
                     ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
                     ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * unit_ch, x0,
                                      y0, n0);
                 }
             }
-            uint32_t acc[32];
-            ptx::tmem_ld_32x32(t_row + sub * 32, acc);
             ptx::tmem_ld_wait();
+            if (sub == BN / 32 - 1) {
+                // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+            }
             float v[32];
             if (p.act == WT_ACT_SILU) {
                 // v * sigmoid(v) with ex2.approx + rcp.approx (2 MUFU): relative error ~1e-6 everywhere.
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float x = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
+                    const float x = __uint_as_float(acc[j]) + bias[sub * 32 + j];
                     v[j] = __fdividef(x, 1.0f + __expf(-x));
                 }
             } else if (p.act == kActSiluTanh) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float h = fmaf(__uint_as_float(acc[j]), 0.5f, sBias[sub * 32 + j]);
+                    const float h = 0.5f * (__uint_as_float(acc[j]) + bias[sub * 32 + j]);
                     v[j] = fmaf(h, tanh_fast(h), h);
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + sBias[sub * 32 + j];
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias[sub * 32 + j];
             }
-            if (p.has_res && sub_in_unit == 0) ptx::mbar_wait(&res_bar[sb], (unit_counter >> 1) & 1);
+            if (p.has_res && sub_in_unit == 0)
+                ptx::mbar_wait(&res_bar[sb], (two_bufs ? (unit_counter >> 1) : unit_counter) & 1);
 
             if (p.out_f32) {
                 // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B
@@ -200,15 +224,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                     *dstp = o;
                 }
             }
-            if (sub == BN / 32 - 1) {
-                // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[ab]);
-            }
             if (sub_in_unit == subs_per_unit - 1) {
                 ptx::fence_proxy_async_smem();
-                ptx::bar_sync(kEpiBarrier, kEpiThreads);
+                ptx::bar_sync(bar_id, kEpiThreads);
                 if (store_thread) {
                     ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * unit_ch, x0, y0, n0);
                     ptx::tma_store_commit();
@@ -223,24 +241,27 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     using L = SmemLayout<BN, BK>;
-    constexpr int kStages = L::kStages;
+    const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
     constexpr uint32_t kTmemCols = 2 * BN;   // double-buffered accumulator (power of two >= 64)
     static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
+    // starts aligned, so no slack bytes are reserved) and checked once
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;                                  // [stages][128][BK] bf16 (swizzled)
     uint8_t* sB = smem + kStages * L::kABytes;           // [stages][BN][BK]  bf16 (swizzled)
-    uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 x 16 KB epilogue staging
-    float* sBias = reinterpret_cast<float*>(sStage + 2 * kStageBufBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
-    uint64_t* full_bar = bars;                       // [stages]  TMA -> MMA
-    uint64_t* empty_bar = bars + kStages;            // [stages]  MMA -> TMA
-    uint64_t* tfull_bar = bars + 2 * kStages;        // [2]       MMA -> epilogue
-    uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]       epilogue -> MMA
-    uint64_t* res_bar = bars + 2 * kStages + 4;      // [2]       residual TMA -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 6);
+    uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 groups x epi_bufs x 16 KB epilogue staging
+    float* sBias = reinterpret_cast<float*>(sStage + kEpiGroups * p.epi_bufs * kStageBufBytes);   // [kMaxCout]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
+    uint64_t* full_bar = bars;                          // [stages]  TMA -> MMA
+    uint64_t* empty_bar = bars + kMaxStages;            // [stages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]       MMA -> epilogue group
+    uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]       epilogue group -> MMA
+    uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2][2]    residual TMA -> epilogue group
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 8);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -259,14 +280,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], 4);
-            ptx::mbar_init(&res_bar[i], 1);
         }
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, kTmemCols);
         ptx::tmem_relinquish();
     }
+    // whole bias vector -> smem once per CTA
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -384,37 +407,34 @@ constexpr int kHaloABytes = ((kHaloW * kHaloH * 128 + 1023) / 1024) * 1024;   //
 
 template <int BN>
 struct HaloSmem {
-    static constexpr int kAStages = 3;
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kFixedBytes = 2 * kStageBufBytes + BN * 4 + 1024;
-    static constexpr int kBudget = 232448 - 1024;
-    static constexpr int kBStagesRaw = (kBudget - kFixedBytes - kAStages * kHaloABytes) / kBBytes;
-    static constexpr int kBStages = kBStagesRaw > 12 ? 12 : kBStagesRaw;
-    static constexpr int kTotalBytes = kAStages * kHaloABytes + kBStages * kBBytes + kFixedBytes + 1024;
-    static_assert(kBStages >= 3, "not enough shared memory for the weight pipeline");
 };
+constexpr int kMaxAStages = 4;
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
     using L = HaloSmem<BN>;
-    constexpr int kAStages = L::kAStages, kBStages = L::kBStages;
+    const int kAStages = p.a_stages, kBStages = p.stages;
     constexpr uint32_t kTmemCols = 2 * BN;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
+    // starts aligned, so no slack bytes are reserved) and checked once
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;                                        // [kAStages] halo tiles (180 px x 128 B, swizzled)
     uint8_t* sB = smem + kAStages * kHaloABytes;               // [kBStages][BN][64] bf16
     uint8_t* sStage = sB + kBStages * L::kBBytes;
-    float* sBias = reinterpret_cast<float*>(sStage + 2 * kStageBufBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+    float* sBias = reinterpret_cast<float*>(sStage + kEpiGroups * p.epi_bufs * kStageBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
     uint64_t* afull = bars;
-    uint64_t* aempty = afull + kAStages;
-    uint64_t* bfull = aempty + kAStages;
-    uint64_t* bempty = bfull + kBStages;
-    uint64_t* tfull_bar = bempty + kBStages;
+    uint64_t* aempty = afull + kMaxAStages;
+    uint64_t* bfull = aempty + kMaxAStages;
+    uint64_t* bempty = bfull + kMaxStages;
+    uint64_t* tfull_bar = bempty + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* res_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -437,14 +457,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
             ptx::mbar_init(&tempty_bar[i], 4);
-            ptx::mbar_init(&res_bar[i], 1);
         }
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_slot, kTmemCols);
         ptx::tmem_relinquish();
     }
+    // whole bias vector -> smem once per CTA
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -538,6 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
 struct ConvTcPlan {
     ConvTcParams prm;
+    int smem_bytes;
     bool halo;
     int bn, bk;
     int pix_per_image_tiles;   // tiles_x * tiles_y
@@ -576,6 +599,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     WT_REQUIRE(d.dst.dtype == WT_DT_BF16 || d.dst.dtype == WT_DT_F32, "conv output must be bf16 or f32");
     const int bn = pick_bn(d.cout);
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
+    WT_REQUIRE(d.cout <= kMaxCout, "cout exceeds the shared-memory bias vector");
     int bk = (d.cin % 64 == 0) ? 64 : 32;
     WT_REQUIRE(d.cin % bk == 0, "cin must be a multiple of 32");
     const int ho = d.dst.h, wo = d.dst.w;
@@ -615,6 +639,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.ksize = d.k;
     p.stride = d.stride;
     p.cin = d.cin;
+    p.cout = d.cout;
     p.cin_blocks = ceil_div(d.cin, bk);
     p.src_coff = d.src.coff;
     p.dst_coff = d.dst.coff;
@@ -626,6 +651,27 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.bias = d.bias;
     p.num_tiles = 0;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
+    // shared-memory plan
+    p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
+    const int fixed = fixed_smem_bytes(p.epi_bufs);
+    if (pl->halo) {
+        p.a_stages = bn == 256 ? 2 : 3;
+        const int b_bytes = bn * 128;
+        p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
+        if (p.stages > 12) p.stages = 12;
+        if (p.stages < 2) {
+            delete pl;
+            set_error("not enough shared memory for the halo weight pipeline");
+            return 1;
+        }
+        pl->smem_bytes = p.a_stages * kHaloABytes + p.stages * b_bytes + fixed;
+    } else {
+        p.a_stages = 0;
+        const int stage_bytes = (kTileM + bn) * bk * 2;
+        p.stages = (kSmemBudget - fixed) / stage_bytes;
+        if (p.stages > kMaxStages) p.stages = kMaxStages;
+        pl->smem_bytes = p.stages * stage_bytes + fixed;
+    }
 
     const int sw_in = bk * 2;   // swizzle span == K-block row bytes
     int rc = 0;
@@ -699,29 +745,27 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
 void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 
 template <int BN, int BK>
-static int launch_inst(const ConvTcParams& prm, int grid, cudaStream_t stream) {
-    using L = SmemLayout<BN, BK>;
+static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         WT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           L::kTotalBytes));
+                                           kSmemBudget));
         configured = true;
     }
-    conv_tc_kernel<BN, BK><<<grid, kThreads, L::kTotalBytes, stream>>>(prm);
+    conv_tc_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(prm);
     WT_LAUNCHED();
     return 0;
 }
 
 template <int BN>
-static int launch_halo(const ConvTcParams& prm, int grid, cudaStream_t stream) {
-    using L = HaloSmem<BN>;
+static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         WT_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           L::kTotalBytes));
+                                           kSmemBudget));
         configured = true;
     }
-    conv_halo_kernel<BN><<<grid, kThreads, L::kTotalBytes, stream>>>(prm);
+    conv_halo_kernel<BN><<<grid, kThreads, smem, stream>>>(prm);
     WT_LAUNCHED();
     return 0;
 }
@@ -734,22 +778,22 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
     if (pl->halo) {
         switch (pl->bn) {
-            case 256: return launch_halo<256>(prm, grid, stream);
-            case 128: return launch_halo<128>(prm, grid, stream);
-            case 64:  return launch_halo<64>(prm, grid, stream);
-            case 32:  return launch_halo<32>(prm, grid, stream);
+            case 256: return launch_halo<256>(prm, pl->smem_bytes, grid, stream);
+            case 128: return launch_halo<128>(prm, pl->smem_bytes, grid, stream);
+            case 64:  return launch_halo<64>(prm, pl->smem_bytes, grid, stream);
+            case 32:  return launch_halo<32>(prm, pl->smem_bytes, grid, stream);
         }
     }
     const int key = pl->bn * 100 + pl->bk;
     switch (key) {
-        case 25664: return launch_inst<256, 64>(prm, grid, stream);
-        case 12864: return launch_inst<128, 64>(prm, grid, stream);
-        case 6464:  return launch_inst<64, 64>(prm, grid, stream);
-        case 3264:  return launch_inst<32, 64>(prm, grid, stream);
-        case 25632: return launch_inst<256, 32>(prm, grid, stream);
-        case 12832: return launch_inst<128, 32>(prm, grid, stream);
-        case 6432:  return launch_inst<64, 32>(prm, grid, stream);
-        case 3232:  return launch_inst<32, 32>(prm, grid, stream);
+        case 25664: return launch_inst<256, 64>(prm, pl->smem_bytes, grid, stream);
+        case 12864: return launch_inst<128, 64>(prm, pl->smem_bytes, grid, stream);
+        case 6464:  return launch_inst<64, 64>(prm, pl->smem_bytes, grid, stream);
+        case 3264:  return launch_inst<32, 64>(prm, pl->smem_bytes, grid, stream);
+        case 25632: return launch_inst<256, 32>(prm, pl->smem_bytes, grid, stream);
+        case 12832: return launch_inst<128, 32>(prm, pl->smem_bytes, grid, stream);
+        case 6432:  return launch_inst<64, 32>(prm, pl->smem_bytes, grid, stream);
+        case 3232:  return launch_inst<32, 32>(prm, pl->smem_bytes, grid, stream);
         default:
             set_error("no conv_tc instantiation for this (BN, BK)");
             return 1;

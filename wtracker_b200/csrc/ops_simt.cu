@@ -52,73 +52,126 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, 
 
 // ------------------------------------------------------------------ first layer
 // u8 grey -> COUT channels, 3x3 stride 2 pad 1, fp32 math.  One thread = 4 horizontally adjacent
-// output pixels x 8 output channels: the 72 weights of its channel group stay in registers (no
-// shared-memory traffic in the FMA loop), the 3 x 9 input bytes are read once, and the four lanes
-// of a pixel quad together store 64 contiguous bytes per pixel.
+// output pixels x 8 output channels, walking kConv0Rows output rows: the 72 weights of its channel
+// group are loaded once and stay in registers, the 3-row input window slides (one 8-byte + one 1-byte
+// load per new input row), and the four lanes of a pixel quad together store 64 contiguous bytes per
+// pixel.  Issue-bound on the FMA/MUFU pipes (~14 instructions per output), not on HBM.
+constexpr int kConv0Rows = 8;
+constexpr int kConv0Threads = 128;
+
+struct Conv0Raw {   // one input row segment as loaded: columns 2*x0 .. 2*x0+7 and column 2*x0-1
+    uint2 v;
+    uint32_t left;
+};
+
+__device__ __forceinline__ Conv0Raw conv0_load_row(const uint8_t* __restrict__ img, int w, int h, int iy, int x0) {
+    Conv0Raw r;
+    r.v = make_uint2(0u, 0u);
+    r.left = 0u;
+    if (iy >= 0 && iy < h) {
+        const uint8_t* rowp = img + size_t(iy) * w + 2 * x0;
+        r.v = __ldg(reinterpret_cast<const uint2*>(rowp));       // 8-byte aligned: w % 8 == 0, x0 % 4 == 0
+        if (x0 > 0) r.left = __ldg(rowp - 1);                    // zero padding at x = -1
+    }
+    return r;
+}
+
+__device__ __forceinline__ void conv0_unpack(const Conv0Raw& r, float (&in)[9]) {
+    in[0] = float(r.left);
+    in[1] = float(r.v.x & 0xFFu);
+    in[2] = float((r.v.x >> 8) & 0xFFu);
+    in[3] = float((r.v.x >> 16) & 0xFFu);
+    in[4] = float(r.v.x >> 24);
+    in[5] = float(r.v.y & 0xFFu);
+    in[6] = float((r.v.y >> 8) & 0xFFu);
+    in[7] = float((r.v.y >> 16) & 0xFFu);
+    in[8] = float(r.v.y >> 24);
+}
+
 template <int COUT>
-__global__ void __launch_bounds__(256) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
-                                                    const float* __restrict__ w9, const float* __restrict__ bias,
-                                                    int act, __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
-                                                    long long total_threads) {
+__global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
+                                                              const float* __restrict__ w9,
+                                                              const float* __restrict__ bias, int act,
+                                                              __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
+                                                              long long total_threads) {
     constexpr int G = COUT / 8;
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= total_threads) return;
     const int g = int(idx % G);
     long long q = idx / G;
     const int ho = h / 2, wo = w / 2, qw = wo / 4;
+    const int strips = (ho + kConv0Rows - 1) / kConv0Rows;
     const int xq = int(q % qw);
     q /= qw;
-    const int y = int(q % ho);
-    const int n = int(q / ho);
+    const int ys = int(q % strips);
+    const int n = int(q / strips);
     const int x0 = xq * 4;
+    const int y_begin = ys * kConv0Rows;
+    const int y_end = min(y_begin + kConv0Rows, ho);
+    const uint8_t* img = src + size_t(n) * h * w;
 
-    float wreg[9][8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) wreg[t][j] = __ldg(w9 + (g * 8 + j) * 9 + t);
-    float acc[4][8];
+    // the first three input rows are in flight while the weights load
+    Conv0Raw raw0 = conv0_load_row(img, w, h, 2 * y_begin - 1, x0);
+    Conv0Raw raw1 = conv0_load_row(img, w, h, 2 * y_begin, x0);
+    Conv0Raw raw2 = conv0_load_row(img, w, h, 2 * y_begin + 1, x0);
+    float wreg[9][8], breg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float b = __ldg(bias + g * 8 + j);
+        breg[j] = __ldg(bias + g * 8 + j);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) acc[p][j] = b;
+        for (int t = 0; t < 9; ++t) wreg[t][j] = __ldg(w9 + (g * 8 + j) * 9 + t);
     }
-    const uint8_t* img = src + size_t(n) * h * w;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int iy = 2 * y + kh - 1;
-        const bool row_ok = iy >= 0 && iy < h;
-        const uint8_t* rowp = img + size_t(row_ok ? iy : 0) * w;
-        float in[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            const int ix = 2 * x0 - 1 + c;
-            in[c] = (row_ok && ix >= 0 && ix < w) ? float(__ldg(rowp + ix)) : 0.f;
-        }
+    float r0[9], r1[9], r2[9];          // input rows 2y-1, 2y, 2y+1
+    conv0_unpack(raw0, r0);
+    for (int y = y_begin; y < y_end; ++y) {
+        conv0_unpack(raw1, r1);
+        conv0_unpack(raw2, r2);
+        // prefetch the next output row's two new input rows a whole iteration ahead (rows past the
+        // strip are only read inside the image, rows past the image return zeros without a load)
+        raw1 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 2, x0);
+        raw2 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 3, x0);
+        float acc[4][8];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int j = 0; j < 8; ++j) acc[p][j] = breg[j];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[2 * p + kw], wreg[kh * 3 + kw][j], acc[p][j]);
-    }
-    __nv_bfloat16* out = dst + ((size_t(n) * ho + y) * wo + x0) * dct + dcoff + g * 8;
+        for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        float o[8];
+            for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = act == WT_ACT_SILU ? silu_f(acc[p][j]) : acc[p][j];
-        uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&t0);
-        pk.y = *reinterpret_cast<uint32_t*>(&t1);
-        pk.z = *reinterpret_cast<uint32_t*>(&t2);
-        pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(out + size_t(p) * dct) = pk;
+                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r0[2 * p + kw], wreg[kw][j], acc[p][j]);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r1[2 * p + kw], wreg[3 + kw][j], acc[p][j]);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r2[2 * p + kw], wreg[6 + kw][j], acc[p][j]);
+        __nv_bfloat16* out = dst + ((size_t(n) * ho + y) * wo + x0) * dct + dcoff + g * 8;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = act == WT_ACT_SILU ? silu_f(acc[p][j]) : acc[p][j];
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(out + size_t(p) * dct) = pk;
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) r0[c] = r2[c];
     }
 }
 
@@ -210,9 +263,10 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
     WT_REQUIRE(h % 2 == 0 && w % 8 == 0, "conv0 needs an even height and a width that is a multiple of 8");
     WT_REQUIRE(dst.dtype == WT_DT_BF16 && dst.h == h / 2 && dst.w == w / 2, "conv0 destination shape");
     WT_REQUIRE(dst.ctot % 8 == 0 && dst.coff % 8 == 0, "conv0 destination channel alignment");
-    const long long total = (long long)n_images * (h / 2) * (w / 8) * (cout / 8);   // pixel quads x channel groups
+    const int strips = (h / 2 + kConv0Rows - 1) / kConv0Rows;
+    const long long total = (long long)n_images * strips * (w / 8) * (cout / 8);   // row strips x pixel quads x channel groups
     if (total == 0) return 0;
-    const int threads = 256;
+    const int threads = kConv0Threads;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dst.base);
     if (cout == 32)
