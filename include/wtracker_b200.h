@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 1
+#define WT_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -89,6 +89,12 @@ typedef struct wt_op {
     int64_t w_off, b_off;        /* byte offsets into the weight blob:                         */
                                  /*   CONV : bf16 [cout][k][k][cin], f32 bias[cout]            */
                                  /*   CONV0: f32 [cout][3][3] (grey-folded, /255 folded), f32 bias */
+    int64_t dot_off;             /* CONV only, -1 = none.  Otherwise the byte offset of        */
+                                 /* f32 [cout + 1] = weights w[cout] then a bias b of a FUSED   */
+                                 /* following 1x1 convolution with ONE output channel (the     */
+                                 /* class-logit conv of the head, nc = 1): the activated output */
+                                 /* is not stored; dst (f32, c = 1) receives                    */
+                                 /* sum_c out[c] * w[c] + b per pixel.  Needs cout <= 256.      */
 } wt_op;
 
 typedef struct wt_engine wt_engine;

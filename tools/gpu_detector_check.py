@@ -37,9 +37,7 @@ for lvl, h in enumerate(eng.program.head):
     rb = feats[lvl][:, :64]
     e = (gb - rb).abs()
     print(f"head{lvl} box logits ref std {rb.std():.3f} | err max {e.max():.4f} mean {e.mean():.5f}")
-    gf = eng.buffer_tensor(h["cls_feat"], n).float().cpu()
-    wc = model.model[22].cv3[lvl][2]
-    glog = (gf @ wc.weight.view(-1).to(torch.bfloat16).float()) + wc.bias
+    glog = eng.buffer_tensor(h["cls_logit"], n)[..., 0].cpu()
     rl = feats[lvl][:, 64]
     e = (glog - rl).abs()
     print(f"head{lvl} cls logit ref mean {rl.mean():.3f} std {rl.std():.3f} max {rl.max():.3f} | err max {e.max():.4f} mean {e.mean():.5f}")

@@ -27,9 +27,23 @@ def timeit(fn, iters=10):
 total_ms = timeit(lambda: eng.forward(batch))
 tot_flop = 2 * eng.arch.macs_per_image(imgsz, imgsz) * batch
 print(f"whole forward: {total_ms:.3f} ms  -> {batch / total_ms * 1e3:.0f} img/s, {tot_flop / total_ms / 1e9:.1f} TFLOP/s")
+# per-op times INSIDE a whole pass (events between consecutive ops), median over passes: every op sees the
+# cache state the real forward gives it (re-running one op back to back would find its input in L2)
+import numpy as np
+reps = 7
+per = np.zeros((reps, len(ops)))
+for r in range(reps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(ops) + 1)]
+    evs[0].record()
+    for i in range(len(ops)):
+        eng.forward(batch, i, i + 1)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    per[r] = [evs[i].elapsed_time(evs[i + 1]) for i in range(len(ops))]
+per = np.median(per, axis=0)
 rows = []
 for i, o in enumerate(ops):
-    ms = timeit(lambda: eng.forward(batch, i, i + 1), 6)
+    ms = float(per[i])
     h, w, c, _ = eng.program.bufs[o["dst"]]
     flop = 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 * batch if o["kind"] in (0, 1) else 0
     rows.append((ms, i, o["name"], o["cin"], o["cout"], o["k"], o["stride"], h, flop))

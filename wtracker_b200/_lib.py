@@ -42,7 +42,7 @@ class WtOp(C.Structure):
         ("cin", C.c_int32), ("cout", C.c_int32),
         ("k", C.c_int32), ("stride", C.c_int32),
         ("act", C.c_int32),
-        ("w_off", C.c_int64), ("b_off", C.c_int64),
+        ("w_off", C.c_int64), ("b_off", C.c_int64), ("dot_off", C.c_int64),
     ]
 
 
@@ -121,7 +121,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 1:
+        if handle.wt_abi_version() != 2:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

@@ -18,6 +18,7 @@ struct ConvDesc {
     int cin, cout, k, stride, act;
     const __nv_bfloat16* w;     // [cout][k][k][cin]
     const float* bias;          // [cout]
+    const float* dot_w;         // fused 1-channel 1x1 head (wt_op.dot_off): f32 [cout + 1], or nullptr
     int batch;                  // images the buffers were sized for
 };
 

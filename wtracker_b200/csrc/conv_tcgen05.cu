@@ -54,6 +54,10 @@ struct ConvTcParams {
     int src_coff, dst_coff, res_coff;
     int act, has_res, out_f32;
     int num_tiles;
+    // fused 1-channel 1x1 head (wt_op.dot_off): out pixel = sum_c act(conv)[c] * dot_w[c] + dot_w[cout]
+    const float* dot_w;
+    float* dot_out;                  // f32 [n][out_h][out_w]
+    int out_w, out_h, n_images;
     // shared-memory plan (host-chosen): pipeline depth and epilogue staging buffers per group (1 | 2).
     // HBM-bound layers (1x1, narrow N) want two staging buffers per epilogue group, MMA-bound layers
     // want the bytes as pipeline stages instead.
@@ -131,6 +135,46 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
 
+        if (p.dot_w) {
+            // fused class-logit head: this thread owns one pixel and all its output channels (n_blocks == 1)
+            const float* dw = sBias + p.cout;
+            float dot = 0.f;
+#pragma unroll 1
+            for (int sub = 0; sub < BN / 32; ++sub) {
+                uint32_t acc[32];
+                ptx::tmem_ld_32x32(t_row + sub * 32, acc);
+                ptx::tmem_ld_wait();
+                if (sub == BN / 32 - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+                }
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + sub * 32 + 4 * j4);
+                    const float4 w = *reinterpret_cast<const float4*>(dw + sub * 32 + 4 * j4);
+                    const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v = __uint_as_float(acc[4 * j4 + e]) + bb[e];
+                        if (p.act == WT_ACT_SILU) {
+                            v = __fdividef(v, 1.0f + __expf(-v));
+                        } else if (p.act == kActSiluTanh) {
+                            const float h = 0.5f * v;
+                            v = fmaf(h, tanh_fast(h), h);
+                        }
+                        dot = fmaf(v, ww[e], dot);
+                    }
+                }
+            }
+            const int px = x0 + row % p.tw;
+            const int py = y0 + (row / p.tw) % p.th;
+            const int pn = n0 + row / (p.tw * p.th);
+            if (px < p.out_w && py < p.out_h && pn < p.n_images)
+                p.dot_out[(size_t(pn) * p.out_h + py) * p.out_w + px] = dot + dw[p.cout];
+            continue;
+        }
+
 #pragma unroll 1
         for (int sub = 0; sub < BN / 32; ++sub) {
             const int sub_in_unit = sub % subs_per_unit;
@@ -160,22 +204,24 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                 if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
             }
             float v[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {   // accumulator + bias (bias read as 8 x LDS.128 broadcasts)
+                const float4 b = *reinterpret_cast<const float4*>(bias + sub * 32 + 4 * j4);
+                v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
+                v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
+                v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
+                v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
+            }
             if (p.act == WT_ACT_SILU) {
                 // v * sigmoid(v) with ex2.approx + rcp.approx (2 MUFU): relative error ~1e-6 everywhere.
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = __uint_as_float(acc[j]) + bias[sub * 32 + j];
-                    v[j] = __fdividef(x, 1.0f + __expf(-x));
-                }
+                for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
             } else if (p.act == kActSiluTanh) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float h = 0.5f * (__uint_as_float(acc[j]) + bias[sub * 32 + j]);
+                    const float h = 0.5f * v[j];
                     v[j] = fmaf(h, tanh_fast(h), h);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias[sub * 32 + j];
             }
             if (p.has_res && sub_in_unit == 0)
                 ptx::mbar_wait(&res_bar[sb], (two_bufs ? (unit_counter >> 1) : unit_counter) & 1);
@@ -290,6 +336,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     // whole bias vector -> smem once per CTA
     for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
+    if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
+        for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -467,6 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
     // whole bias vector -> smem once per CTA
     for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
+    if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
+        for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -610,9 +660,13 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     }
     const bool out_f32 = d.dst.dtype == WT_DT_F32;
     WT_REQUIRE(!(out_f32 && d.res.base), "residual only with bf16 output");
+    if (d.dot_w) {
+        WT_REQUIRE(bn == d.cout && 2 * d.cout + 1 <= kMaxCout, "a dot-head conv needs all channels in one N tile");
+        WT_REQUIRE(out_f32 && d.dst.ctot == 1 && !d.res.base, "a dot-head conv writes a 1-channel f32 buffer");
+    }
     // TMA needs 16-byte aligned global strides and base addresses
     WT_REQUIRE((d.src.ctot * 2) % 16 == 0 && (d.src.coff * 2) % 16 == 0, "source channel alignment");
-    WT_REQUIRE((d.dst.ctot * (out_f32 ? 4 : 2)) % 16 == 0, "destination channel alignment");
+    WT_REQUIRE(d.dot_w || (d.dst.ctot * (out_f32 ? 4 : 2)) % 16 == 0, "destination channel alignment");
 
     ConvTcPlan* pl = new ConvTcPlan();
     ConvTcParams& p = pl->prm;
@@ -649,6 +703,11 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.has_res = d.res.base ? 1 : 0;
     p.out_f32 = out_f32 ? 1 : 0;
     p.bias = d.bias;
+    p.dot_w = d.dot_w;
+    p.dot_out = d.dot_w ? static_cast<float*>(d.dst.base) : nullptr;
+    p.out_w = wo;
+    p.out_h = ho;
+    p.n_images = 0;
     p.num_tiles = 0;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     // shared-memory plan
@@ -710,7 +769,10 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
     }
-    {
+    if (d.dot_w) {
+        p.tmD = p.tmA[0];   // never used: the dot head stores with plain st.global
+        p.tmR = p.tmA[0];
+    } else {
         const int es = out_f32 ? 4 : 2;
         const int unit_ch = out_f32 ? 32 : (bn == 32 ? 32 : 64);
         const int sw = unit_ch * es;   // 128 or 64
@@ -774,6 +836,7 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     ConvTcParams prm = pl->prm;
     const int tiles_n = ceil_div(n_images, prm.tn);
     prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;
+    prm.n_images = n_images;
     if (prm.num_tiles == 0) return 0;
     const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
     if (pl->halo) {

@@ -3,14 +3,20 @@
 #include "../../include/wtracker_b200.h"
 #include "conv.cuh"
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace wt {
 
 static int64_t dtype_size(int dt) { return dt == WT_DT_F32 ? 4 : (dt == WT_DT_U8 ? 1 : 2); }
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static int64_t buf_align() {
+    static const int64_t a = getenv("WT_BUF_ALIGN") ? atoll(getenv("WT_BUF_ALIGN")) : 1024;
+    return a;
+}
 static int64_t buf_bytes(const wt_buf& b, int batch) {
-    return align_up(int64_t(batch) * b.h * b.w * b.c * dtype_size(b.dtype), 1024);
+    return align_up(int64_t(batch) * b.h * b.w * b.c * dtype_size(b.dtype), buf_align());
 }
 
 }  // namespace wt
@@ -45,7 +51,7 @@ static TensorView view_of(const wt_engine* e, int id, int coff) {
 extern "C" int64_t wt_engine_workspace_bytes(const wt_buf* bufs, int n_bufs, int batch) {
     int64_t total = 0;
     for (int i = 0; i < n_bufs; ++i) total += buf_bytes(bufs[i], batch);
-    return total + 1024;
+    return total + buf_align();
 }
 
 extern "C" void wt_engine_destroy(wt_engine* e) {
@@ -73,7 +79,7 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
     e->weight_bytes = weight_bytes;
     e->bufs.assign(bufs, bufs + n_bufs);
     e->ops.assign(ops, ops + n_ops);
-    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<int64_t>(workspace), 1024));
+    uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<int64_t>(workspace), buf_align()));
     for (int i = 0; i < n_bufs; ++i) {
         e->buf_ptr.push_back(ws);
         ws += buf_bytes(bufs[i], batch);
@@ -107,8 +113,16 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             d.act = o.act;
             d.w = reinterpret_cast<const __nv_bfloat16*>(e->weights + o.w_off);
             d.bias = reinterpret_cast<const float*>(e->weights + o.b_off);
+            d.dot_w = nullptr;
+            if (o.dot_off >= 0) {
+                if (o.dot_off % 4 != 0 || o.dot_off + int64_t(o.cout + 1) * 4 > weight_bytes)
+                    return fail("dot-head weights out of range", i);
+                if (e->bufs[o.dst].dtype != WT_DT_F32 || e->bufs[o.dst].c != 1 || o.dst_coff != 0 || o.res >= 0)
+                    return fail("a dot-head conv writes a 1-channel f32 buffer and has no residual", i);
+                d.dot_w = reinterpret_cast<const float*>(e->weights + o.dot_off);
+            }
             d.batch = batch;
-            if (o.src_coff + o.cin > e->bufs[o.src].c || o.dst_coff + o.cout > e->bufs[o.dst].c)
+            if (o.src_coff + o.cin > e->bufs[o.src].c || (!d.dot_w && o.dst_coff + o.cout > e->bufs[o.dst].c))
                 return fail("channel slice exceeds buffer", i);
             if (conv_impl == 0) {
                 if (conv_tc_plan_create(d, &e->conv_plan[i])) {
@@ -228,7 +242,7 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     d.dst = TensorView{d_out_tc, ho, wo, dst_ct, dst_off, out_f32 ? WT_DT_F32 : WT_DT_BF16};
     d.res = with_residual ? TensorView{d_res, ho, wo, dst_ct, dst_off, WT_DT_BF16} : TensorView{nullptr, 0, 0, 0, 0, 0};
     d.cin = cin; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
-    d.w = d_w; d.bias = d_bias; d.batch = batch;
+    d.w = d_w; d.bias = d_bias; d.dot_w = nullptr; d.batch = batch;
     ConvTcPlan* plan = nullptr;
     int rc = conv_tc_plan_create(d, &plan);
     if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);

@@ -50,6 +50,40 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, 
     else static_cast<__nv_bfloat16*>(dst)[opix * dct + dcoff + co] = __float2bfloat16_rn(v);
 }
 
+// scalar validation of a conv with a fused 1-channel head: one thread per pixel walks all channels
+__global__ void conv_dot_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sct, int scoff,
+                                     float* __restrict__ dst, int dh, int dw, const __nv_bfloat16* __restrict__ wgt,
+                                     const float* __restrict__ bias, const float* __restrict__ dot_w, int cin, int cout,
+                                     int k, int stride, int act, long long total) {
+    long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= total) return;
+    const long long opix = pix;
+    const int x = int(pix % dw);
+    pix /= dw;
+    const int y = int(pix % dh);
+    const int n = int(pix / dh);
+    const int pad = k / 2;
+    float dot = 0.f;
+    for (int co = 0; co < cout; ++co) {
+        float acc = 0.f;
+        for (int kh = 0; kh < k; ++kh) {
+            const int iy = y * stride + kh - pad;
+            if (iy < 0 || iy >= sh) continue;
+            for (int kw = 0; kw < k; ++kw) {
+                const int ix = x * stride + kw - pad;
+                if (ix < 0 || ix >= sw) continue;
+                const __nv_bfloat16* ip = src + ((size_t(n) * sh + iy) * sw + ix) * sct + scoff;
+                const __nv_bfloat16* wp = wgt + ((size_t(co) * k + kh) * k + kw) * cin;
+                for (int c = 0; c < cin; ++c) acc = fmaf(__bfloat162float(ip[c]), __bfloat162float(wp[c]), acc);
+            }
+        }
+        float v = acc + bias[co];
+        if (act == WT_ACT_SILU) v = silu_f(v);
+        dot = fmaf(v, dot_w[co], dot);
+    }
+    dst[opix] = dot + dot_w[cout];
+}
+
 // ------------------------------------------------------------------ first layer
 // u8 grey -> COUT channels, 3x3 stride 2 pad 1, fp32 math.  One thread = 4 horizontally adjacent
 // output pixels x 8 output channels, walking kConv0Rows output rows: the 72 weights of its channel
@@ -244,6 +278,16 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int sh,
 
 int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream) {
     WT_REQUIRE(d.src.dtype == WT_DT_BF16, "conv input must be bf16");
+    if (d.dot_w) {
+        const long long pixels = (long long)n_images * d.dst.h * d.dst.w;
+        if (pixels == 0) return 0;
+        conv_dot_simt_kernel<<<(unsigned)((pixels + 127) / 128), 128, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(d.src.base), d.src.h, d.src.w, d.src.ctot, d.src.coff,
+            static_cast<float*>(d.dst.base), d.dst.h, d.dst.w, d.w, d.bias, d.dot_w, d.cin, d.cout, d.k, d.stride, d.act,
+            pixels);
+        WT_LAUNCHED();
+        return 0;
+    }
     const long long total = (long long)n_images * d.dst.h * d.dst.w * d.cout;
     if (total == 0) return 0;
     const int threads = 256;

@@ -73,9 +73,8 @@ class DetectorEngine:
                                        device=self.device)
             levels = (L.WtHeadLevel * 3)()
             for i, h in enumerate(self.program.head):
-                levels[i] = L.WtHeadLevel(self.buffer_ptr(h["box"]), self.buffer_ptr(h["cls_feat"]), None, h["h"],
-                                          h["w"], h["stride"], L.WT_DT_F32, self.arch.cls_c,
-                                          self.weights.data_ptr() + h["cls_w_off"], h["cls_b"])
+                levels[i] = L.WtHeadLevel(self.buffer_ptr(h["box"]), None, self.buffer_ptr(h["cls_logit"]), h["h"],
+                                          h["w"], h["stride"], L.WT_DT_F32, 0, None, 0.0)
             self._levels = levels
             pad_x, pad_y = self.lb.scale_pad
             self._post = L.WtPostParams(self.conf, self.iou, self.max_det, self.lb.dst_w, self.lb.dst_h,

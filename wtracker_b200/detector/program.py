@@ -11,7 +11,8 @@ Layout decisions:
   * the first conv sees three identical grey channels scaled by 1/255, so its weights are summed
     over the input channels and divided by 255 on the host and it runs on the u8 image directly;
   * the last 1x1 of the box branch writes fp32 (DFL is sensitive to logit rounding); the last 1x1
-    of the class branch (cout = nc = 1) is a dot product fused into the decode kernel.
+    of the class branch (cout = nc = 1) is a dot product fused into the epilogue of the 3x3 conv
+    before it (wt_op.dot_off), which then writes one fp32 logit per anchor.
 """
 
 from __future__ import annotations
@@ -73,13 +74,18 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
         p.blob.extend(b.float().numpy().tobytes())
         return w_off, b_off
 
-    def conv(name: str, src: tuple[int, int], dst: tuple[int, int], res: tuple[int, int] | None = None):
+    def conv(name: str, src: tuple[int, int], dst: tuple[int, int], res: tuple[int, int] | None = None,
+             dot: tuple[torch.Tensor, float] | None = None):
         s = specs[name]
         w_off, b_off = add_weights(s)
+        dot_off = -1
+        if dot is not None:     # fused 1-channel 1x1 head: f32 [cout] weights then the bias
+            dot_off = _align(p.blob, 16)
+            p.blob.extend(torch.cat([dot[0].reshape(-1).float(), torch.tensor([dot[1]])]).numpy().tobytes())
         p.ops.append(dict(kind=L.WT_OP_CONV, name=name, src=src[0], src_coff=src[1], dst=dst[0], dst_coff=dst[1],
                           res=-1 if res is None else res[0], res_coff=0 if res is None else res[1], cin=s.cin,
                           cout=s.cout, k=s.k, stride=s.stride, act=L.WT_ACT_SILU if s.bn_act else L.WT_ACT_NONE,
-                          w_off=w_off, b_off=b_off))
+                          w_off=w_off, b_off=b_off, dot_off=dot_off))
 
     def c2f(idx: int, src: tuple[int, int], dst: tuple[int, int], down: int):
         spec = arch.c2f[idx]
@@ -152,17 +158,16 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
         t2 = new_buf(f"head{lvl}.box2", down, arch.box_c)
         box = new_buf(f"head{lvl}.box", down, 4 * REG_MAX, L.WT_DT_F32)
         u1 = new_buf(f"head{lvl}.cls1", down, arch.cls_c)
-        u2 = new_buf(f"head{lvl}.cls2", down, arch.cls_c)
+        logit = new_buf(f"head{lvl}.cls", down, 1, L.WT_DT_F32)
         conv(f"model.22.cv2.{lvl}.0", (feat, 0), (t1, 0))
         conv(f"model.22.cv2.{lvl}.1", (t1, 0), (t2, 0))
         conv(f"model.22.cv2.{lvl}.2", (t2, 0), (box, 0))
         conv(f"model.22.cv3.{lvl}.0", (feat, 0), (u1, 0))
-        conv(f"model.22.cv3.{lvl}.1", (u1, 0), (u2, 0))
+        # the class branch ends in a 1x1 conv with nc = 1 output: a dot product fused into the epilogue of
+        # the conv before it (fp32 weights on the fp32 accumulator, the 128-channel feature map is never stored)
         wc, bc = folded_conv(sd, specs[f"model.22.cv3.{lvl}.2"])
-        cw_off = _align(p.blob, 16)
-        p.blob.extend(wc.reshape(-1).to(torch.bfloat16).view(torch.int16).numpy().tobytes())
-        p.head.append(dict(box=box, cls_feat=u2, cls_w_off=cw_off, cls_b=float(bc.reshape(-1)[0]), h=net_h // down,
-                           w=net_w // down, stride=STRIDES[lvl]))
+        conv(f"model.22.cv3.{lvl}.1", (u1, 0), (logit, 0), dot=(wc, float(bc.reshape(-1)[0])))
+        p.head.append(dict(box=box, cls_logit=logit, h=net_h // down, w=net_w // down, stride=STRIDES[lvl]))
     _align(p.blob, 16)
 
     p.taps = {
@@ -178,7 +183,7 @@ def ops_as_ctypes(p: Program):
     ops = (L.WtOp * len(p.ops))()
     for i, o in enumerate(p.ops):
         ops[i] = L.WtOp(o["kind"], o["src"], o["src_coff"], o["dst"], o["dst_coff"], o["res"], o["res_coff"],
-                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"])
+                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1))
     return bufs, ops
 
 
