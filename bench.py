@@ -285,14 +285,16 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
         views = np.stack([synth.camera_view(frames_np[p], (int(x) + VIEW // 2, int(y) + VIEW // 2), VIEW)
                           for p, x, y in zip(pool, cx, cy)])
         host_batches.append(torch.from_numpy(np.ascontiguousarray(views)).pin_memory())
-    for s in range(min(W, 3)):
-        hp.step_host(host_batches[s % 4], first_row=0)
+    for _ in hp.run_host((host_batches[s % 4] for s in range(max(W, 3)))):     # warm-up (streams, pinned slots)
+        pass
     barrier()
     t0 = time.perf_counter()
-    for s in range(K):
-        hp.step_host(host_batches[s % 4], first_row=(s % 8) * B)
+    n_out = 0
+    for out in hp.run_host((host_batches[s % 4] for s in range(K))):
+        n_out += int(out["count"].shape[0])          # every batch's results are read on the host
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert n_out == K * B
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -345,7 +347,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
         },
         "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": hp.h2d_bytes_per_step,
                 "d2h_bytes_per_step": hp.d2h_bytes_per_step,
-                "api": "HotPath.step_host(pinned u8 views) -> host result arrays"},
+                "api": "HotPath.run_host(iterator of pinned u8 view batches) -> host result arrays per batch (3-stream pipeline: H2D | detect | rows+ResMLP+D2H)"},
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "stage_ms": {"pre": float(stage_ms[0]), "yolo_forward": float(stage_ms[1]), "decode_nms": float(stage_ms[2]),

@@ -1,2 +1,4 @@
 export PYTHONPATH=$PWD
-python tools/gpu_layer_times.py 64 640 > gpurun_out/layers_u7.log 2>&1; head -2 gpurun_out/layers_u7.log
+bash tools/gpu_round.sh u8
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_u8.log 2>gpurun_out/bench_u8.err; tail -3 gpurun_out/bench_u8.err
+python -c "import json; d=json.loads(open('gpurun_out/bench_u8.log').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'], d['gpu_launches'])"

@@ -64,6 +64,9 @@ struct ConvTcParams {
     int stages;        // generic kernel: A+B stages; halo kernel: weight (B) stages
     int a_stages;      // halo kernel: halo-tile stages
     int epi_bufs;
+    // halo kernel: the layer's whole weight set (9 taps x one 64-channel block x all cout) fits in the B
+    // stages, so it is loaded ONCE per CTA and stays resident: no weight re-streaming from L2 per tile
+    int resident;
 };
 
 template <int BN, int BK>
@@ -542,6 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 }
                 __syncwarp();
                 if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                if (p.resident && tile != blockIdx.x) continue;   // weights already in shared memory
                 for (int tap = 0; tap < 9; ++tap) {
                     ptx::mbar_wait(&bempty[sb], pb ^ 1);
                     if (ptx::elect_one()) {
@@ -569,10 +573,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 ptx::mbar_wait(&afull[sa], pa);
                 const uint32_t a_base = sA_u32 + sa * kHaloABytes;
+                const bool wait_b = !p.resident || tile == blockIdx.x;
+                ptx::tc_fence_after();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    ptx::mbar_wait(&bfull[sb], pb);
-                    ptx::tc_fence_after();
+                    if (wait_b) {
+                        ptx::mbar_wait(&bfull[sb], pb);
+                        ptx::tc_fence_after();
+                    }
                     if (ptx::elect_one()) {
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const uint64_t a_desc = ptx::make_kmajor_desc_sbo(a_base + (kh * kHaloW + kw) * 128, kHaloW * 128);
@@ -580,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (cb | tap | kk) != 0);
-                        ptx::umma_commit(&bempty[sb]);
+                        if (!p.resident) ptx::umma_commit(&bempty[sb]);
                         if (tap == 8) {
                             ptx::umma_commit(&aempty[sa]);
                             if (cb == p.cin_blocks - 1) ptx::umma_commit(&tfull_bar[ab]);
@@ -634,12 +642,22 @@ static void choose_patch(int w, int h, int batch, int* tw, int* th, int* tn) {
     }
 }
 
-static int pick_bn(int cout) {
-    if (cout % 256 == 0) return 256;
-    if (cout % 128 == 0) return 128;
-    if (cout % 64 == 0) return 64;
-    if (cout % 32 == 0) return 32;
-    return 0;
+// N tile: the widest one dividing cout, unless a narrower one needs fewer tile waves on this GPU (a 20x20
+// map at batch 64 is 200 pixel tiles: one 256-wide wave and a 52-tile tail cost more than three 128-wide waves).
+static int pick_bn(int cout, long long m_tiles, int sm_count) {
+    int best = 0;
+    long long best_cost = 0;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+        if (cout % bn != 0) continue;
+        const long long tiles = m_tiles * (cout / bn);
+        const long long waves = (tiles + sm_count - 1) / sm_count;
+        const long long cost = waves * (bn + 32);   // per-tile time ~ N plus a fixed part
+        if (best == 0 || cost < best_cost) {
+            best = bn;
+            best_cost = cost;
+        }
+    }
+    return best;
 }
 
 int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
@@ -647,12 +665,24 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     WT_REQUIRE(d.stride == 1 || (d.stride == 2 && d.k == 3), "stride 2 needs a 3x3 kernel");
     WT_REQUIRE(d.src.dtype == WT_DT_BF16, "conv input must be bf16");
     WT_REQUIRE(d.dst.dtype == WT_DT_BF16 || d.dst.dtype == WT_DT_F32, "conv output must be bf16 or f32");
-    const int bn = pick_bn(d.cout);
+    const int ho = d.dst.h, wo = d.dst.w;
+    int sm_count = 148;
+    wt_device_info(&sm_count, nullptr, nullptr);
+    const bool halo_shape = d.k == 3 && d.stride == 1 && (d.cin % 64 == 0 || d.cin == 32) && wo % 8 == 0 &&
+                            ceil_div(ho, 16) * 16 * 4 <= ho * 5;
+    long long m_tiles;
+    if (halo_shape) {
+        m_tiles = (long long)ceil_div(wo, 8) * ceil_div(ho, 16) * d.batch;
+    } else {
+        int tw, th, tn;
+        choose_patch(wo, ho, d.batch, &tw, &th, &tn);
+        m_tiles = (long long)ceil_div(wo, tw) * ceil_div(ho, th) * ceil_div(d.batch, tn);
+    }
+    const int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0) : pick_bn(d.cout, m_tiles, sm_count);
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
     WT_REQUIRE(d.cout <= kMaxCout, "cout exceeds the shared-memory bias vector");
     int bk = (d.cin % 64 == 0) ? 64 : 32;
     WT_REQUIRE(d.cin % bk == 0, "cin must be a multiple of 32");
-    const int ho = d.dst.h, wo = d.dst.w;
     if (d.stride == 1) {
         WT_REQUIRE(d.src.h == ho && d.src.w == wo, "stride-1 conv keeps the spatial size");
     } else {
@@ -675,8 +705,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
     // map height wastes more than a quarter of the 16-row tiles (20x20 maps stay on the generic kernel)
     static const int halo_env = getenv("WT_CONV_HALO") ? atoi(getenv("WT_CONV_HALO")) : 1;
-    pl->halo = halo_env != 0 && d.k == 3 && d.stride == 1 && (d.cin % 64 == 0 || d.cin == 32) && wo % 8 == 0 &&
-               ceil_div(ho, 16) * 16 * 4 <= ho * 5;
+    pl->halo = halo_env != 0 && halo_shape;
     if (pl->halo) {
         bk = 64;
         pl->bk = 64;
@@ -718,6 +747,13 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const int b_bytes = bn * 128;
         p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
         if (p.stages > 12) p.stages = 12;
+        static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
+        p.resident = (resident_env && p.cin_blocks == 1 && p.n_blocks == 1 && p.stages >= 9) ? 1 : 0;
+        if (p.resident) {
+            p.stages = 9;   // the ring wraps once per tile: stage index == tap
+            const int spare = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
+            p.a_stages = spare > kMaxAStages ? kMaxAStages : spare;
+        }
         if (p.stages < 2) {
             delete pl;
             set_error("not enough shared memory for the halo weight pipeline");
@@ -726,6 +762,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         pl->smem_bytes = p.a_stages * kHaloABytes + p.stages * b_bytes + fixed;
     } else {
         p.a_stages = 0;
+        p.resident = 0;
         const int stage_bytes = (kTileM + bn) * bk * 2;
         p.stages = (kSmemBudget - fixed) / stage_bytes;
         if (p.stages > kMaxStages) p.stages = kMaxStages;

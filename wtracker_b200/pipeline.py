@@ -71,8 +71,13 @@ class HotPath:
         written to rows [first_row, first_row + n) of the on-device tracking table."""
         n = int(frame_idx.numel())
         assert n <= self.batch and first_row + n <= self.table_rows
-        s = torch.cuda.current_stream().cuda_stream
         boxes, count = self.det.detect_crops(frames, frame_idx, crop_x, crop_y, marks)
+        return self._rows_mlp_error(boxes, count, crop_x, crop_y, first_row, n)
+
+    def _rows_mlp_error(self, boxes: torch.Tensor, count: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor,
+                        first_row: int, n: int) -> StepResult:
+        """Tracking rows -> ResMLP input gather -> ResMLP -> bbox error on the current stream."""
+        s = torch.cuda.current_stream().cuda_stream
         worm = self.table[first_row: first_row + n]
         mic = self.mic_table[first_row: first_row + n]
         L.check(self.lib.wt_track_rows(boxes.data_ptr(), count.data_ptr(), self.det.max_det, crop_x.data_ptr(),
@@ -109,6 +114,96 @@ class HotPath:
         torch.cuda.current_stream().synchronize()
         return dict(worm=self.h_worm[:n].numpy(), boxes=self.h_boxes[:n].numpy(), count=self.h_count[:n].numpy(),
                     pred=self.h_pred[:n].numpy(), pred_valid=self.h_valid[:n].numpy(), bbox_error=self.h_err[:n].numpy())
+
+    # ------------------------------------------------------------------ pipelined host-buffer path
+    def _make_slots(self):
+        d, B, md = self.device, self.batch, self.det.max_det
+        self._slots = []
+        for _ in range(2):
+            self._slots.append(dict(
+                d_views=torch.empty((B, self.view, self.view), dtype=torch.uint8, device=d),
+                h_worm=torch.empty((B, 4), dtype=torch.float64).pin_memory(),
+                h_boxes=torch.empty((B, md, 6), dtype=torch.float32).pin_memory(),
+                h_count=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                h_pred=torch.empty((B, 2), dtype=torch.float32).pin_memory(),
+                h_valid=torch.empty((B,), dtype=torch.uint8).pin_memory(),
+                h_err=torch.empty((B,), dtype=torch.float64).pin_memory(),
+                ev_h2d=torch.cuda.Event(), ev_in_free=torch.cuda.Event(), ev_out=torch.cuda.Event(), n=0))
+        self._s_copy = torch.cuda.Stream(device=d)
+        self._s_post = torch.cuda.Stream(device=d)
+
+    def run_host(self, batches, first_row: int = 0):
+        """Pipelined form of ``step_host`` for a stream of batches (the public throughput API).
+
+        ``batches`` yields u8 [n, view, view] HOST arrays (pinned torch tensors are copied straight from
+        where they are; anything else goes through a pinned staging buffer first).  Three CUDA streams
+        overlap the work of consecutive batches: host->device copy of batch i+1 || crop + YOLOv8s + decode/NMS
+        of batch i || tracking rows + ResMLP + bbox error + device->host copy of batch i-1.  Every batch still
+        pays its own H2D and D2H inside the call.  Yields one result dict per batch, in order, with the same
+        keys as ``step_host``; the arrays are views of pinned buffers that stay valid until the generator is
+        advanced twice more.  Results of batch i land in rows [first_row + i * batch, ...) of the tracking
+        table (modulo the table size, batch-aligned)."""
+        if not hasattr(self, "_slots"):
+            self._make_slots()
+        main = torch.cuda.current_stream(self.device)
+        slots_rows = max(1, self.table_rows // self.batch)
+        pending = None           # (slot, n) whose results have been enqueued but not yet handed out
+        prev_out = None          # ev_out of the previous batch: guards the detector's single output buffers
+        i = 0
+        for views in batches:
+            sl = self._slots[i & 1]
+            n = int(views.shape[0])
+            assert n <= self.batch
+            src = views if torch.is_tensor(views) else torch.from_numpy(views)
+            if not src.is_pinned():
+                self.h_views[:n].copy_(src)
+                src = self.h_views[:n]
+            row0 = ((first_row // self.batch + i) % slots_rows) * self.batch
+            # ---- copy stream: H2D once the crop kernel of batch i-2 has consumed this slot
+            with torch.cuda.stream(self._s_copy):
+                if i >= 2:
+                    self._s_copy.wait_event(sl["ev_in_free"])
+                sl["d_views"][:n].copy_(src, non_blocking=True)
+                sl["ev_h2d"].record(self._s_copy)
+            # ---- main stream: crop -> YOLOv8s -> decode/NMS
+            main.wait_event(sl["ev_h2d"])
+            det = self.det
+            det.preprocess(sl["d_views"], self._iota[:n], self._zeros[:n], self._zeros[:n], n)
+            sl["ev_in_free"].record(main)
+            det.forward(n)
+            if prev_out is not None:
+                main.wait_event(prev_out)     # the previous batch's rows / D2H have read out_boxes, out_count
+            det.postprocess(n)
+            ev_det = torch.cuda.Event()
+            ev_det.record(main)
+            # ---- post stream: tracking rows -> ResMLP -> bbox error -> D2H
+            with torch.cuda.stream(self._s_post):
+                self._s_post.wait_event(ev_det)
+                r = self._rows_mlp_error(det.out_boxes[:n], det.out_count[:n], self._zeros[:n], self._zeros[:n], row0, n)
+                sl["h_worm"][:n].copy_(r.worm, non_blocking=True)
+                sl["h_boxes"][:n].copy_(r.boxes, non_blocking=True)
+                sl["h_count"][:n].copy_(r.count, non_blocking=True)
+                sl["h_pred"][:n].copy_(r.pred, non_blocking=True)
+                sl["h_valid"][:n].copy_(r.pred_valid, non_blocking=True)
+                sl["h_err"][:n].copy_(r.bbox_error, non_blocking=True)
+                sl["ev_out"].record(self._s_post)
+            sl["n"] = n
+            prev_out = sl["ev_out"]
+            if pending is not None:
+                yield self._collect(pending)
+            pending = sl
+            i += 1
+        if pending is not None:
+            yield self._collect(pending)
+        main.wait_stream(self._s_post)
+
+    @staticmethod
+    def _collect(sl) -> dict[str, np.ndarray]:
+        sl["ev_out"].synchronize()
+        n = sl["n"]
+        return dict(worm=sl["h_worm"][:n].numpy(), boxes=sl["h_boxes"][:n].numpy(), count=sl["h_count"][:n].numpy(),
+                    pred=sl["h_pred"][:n].numpy(), pred_valid=sl["h_valid"][:n].numpy(),
+                    bbox_error=sl["h_err"][:n].numpy())
 
     @property
     def h2d_bytes_per_step(self) -> int:
