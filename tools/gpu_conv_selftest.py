@@ -31,6 +31,10 @@ CASES = [
     (2, 80, 80, 64, 64, 1, 1, 0, 0, 1),      # head box logits f32
     (8, 160, 160, 32, 64, 3, 2, 1, 0, 0),    # many tiles per CTA (persistence, phases)
     (16, 80, 80, 128, 128, 3, 1, 1, 0, 0),
+    (48, 80, 80, 64, 64, 3, 1, 1, 1, 0),     # resident weights, two MMA issuers, ~16 tiles per CTA, residual
+    (40, 160, 160, 32, 32, 3, 1, 1, 1, 0),   # BN 32 resident, ~110 tiles per CTA
+    (64, 40, 40, 256, 128, 3, 1, 1, 0, 0),   # 4 halo blocks per tile, streamed weights
+    (64, 20, 20, 512, 512, 1, 1, 1, 0, 0),   # many K blocks per tile through a short ring
 ]
 
 SNIPPET = """

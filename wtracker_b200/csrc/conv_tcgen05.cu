@@ -14,10 +14,12 @@
 // K-major descriptor expects.  Stride-2 convs use four parity views of the input (even/odd rows x
 // even/odd columns), so each tap is again a dense box.
 //
-// Warp roles (320 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer and
-// TMEM owner, warps 2..5 / 6..9 = two epilogue groups (TMEM -> registers -> swizzled smem -> TMA
-// store).  The TMEM accumulator is double-buffered and each epilogue group owns one buffer, so the
-// epilogues of tiles i and i+1 overlap each other and the main loop of tile i+2.
+// Warp roles (352 threads, persistent over tiles): warp 0 = TMA producer, warps 1..2 = MMA issuers
+// (warp 1 also owns the TMEM allocation), warps 3..6 / 7..10 = two epilogue groups (TMEM -> registers
+// -> swizzled smem -> TMA store).  The TMEM accumulator is double-buffered; MMA issuer w and epilogue
+// group w own buffer w, i.e. every second tile of the CTA.  Two issuers because ONE thread cannot issue
+// narrow MMAs fast enough (measured: ~9 uniform-datapath instructions at ~8-10 clk each per UMMA,
+// while a 128x64x16 UMMA occupies the tensor pipe for only 32 clk).
 #include "../../include/wtracker_b200.h"
 #include "conv.cuh"
 #include "ptx.cuh"
@@ -31,7 +33,9 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kEpiGroups = 2;           // epilogue warp groups; group g drains TMEM accumulator g (tiles it % 2 == g)
 constexpr int kEpiThreads = 128;        // threads per epilogue group (4 warps = the 4 TMEM lane quadrants)
-constexpr int kThreads = 64 + kEpiGroups * kEpiThreads;
+constexpr int kMmaWarps = 2;            // MMA issuer warps; issuer w owns accumulator w (tiles it % 2 == w)
+constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+constexpr int kThreads = kFirstEpiWarp * 32 + kEpiGroups * kEpiThreads;
 constexpr int kEpiBarrier = 1;          // named barrier ids kEpiBarrier + group
 constexpr int kStageBufBytes = 16384;   // one epilogue staging buffer: 128 rows x 128 B
 constexpr int kSmemBudget = 232448;   // 227 KB opt-in maximum per CTA
@@ -67,6 +71,10 @@ struct ConvTcParams {
     // halo kernel: the layer's whole weight set (9 taps x one 64-channel block x all cout) fits in the B
     // stages, so it is loaded ONCE per CTA and stays resident: no weight re-streaming from L2 per tile
     int resident;
+    // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
+    // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
+    // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
+    int issuers;
 };
 
 template <int BN, int BK>
@@ -107,8 +115,8 @@ template <int BN>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
                                               uint32_t tmem_base, int warp, int lane) {
-    const int g = (warp - 2) >> 2;          // epilogue group == accumulator buffer
-    const int et = threadIdx.x - 64 - g * kEpiThreads;   // 0..127 inside the group
+    const int g = (warp - kFirstEpiWarp) >> 2;          // epilogue group == accumulator buffer
+    const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;   // 0..127 inside the group
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
     const bool store_thread = (et == 0);
@@ -392,41 +400,53 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        // Warp-uniform loop; one elected lane issues the UMMAs and the commits.
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
-        const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int ab = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);   // epilogue has drained this accumulator
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + ab * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                ptx::mbar_wait(&full_bar[stage], phase);
+    } else if (warp < kFirstEpiWarp) {
+        // ------------------------------------------------------------------ MMA issuers (warps 1, 2)
+        // ONE elected lane per issuer warp runs the whole loop (waits included).  elect.sync tells the
+        // compiler that a single thread is active, so descriptors and barrier addresses stay on the
+        // uniform datapath; the descriptor low words advance by plain 32-bit adds (stage, K slice).
+        // Issuer w handles tiles it = w, w + 2, ...; both walk the same smem ring, whose slot for the
+        // g-th K block of the CTA is g % stages.
+        const int w = warp - 1;
+        if (w < p.issuers && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+            const uint64_t a_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sA));
+            const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
+            const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
+            const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
+            int it = w;
+            for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles;
+                 tile += p.issuers * gridDim.x, it += p.issuers) {
+                const int ab = it & 1;
+                const uint32_t d_tmem = tmem_base + ab * BN;
+                const uint32_t g0 = uint32_t(it) * uint32_t(num_kb);
+                int stage = int(g0 % uint32_t(kStages));
+                uint32_t phase = (g0 / uint32_t(kStages)) & 1u;
+                uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
+                ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
-                if (ptx::elect_one()) {
-                    const uint64_t a_desc = ptx::make_kmajor_desc<kRowBytes>(sA_u32 + stage * L::kABytes);
-                    const uint64_t b_desc = ptx::make_kmajor_desc<kRowBytes>(sB_u32 + stage * L::kBBytes);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
-                        // advance 16 bf16 = 32 B along K inside the swizzle span: start address += 2
-                        ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0);
+                        // advance 16 bf16 = 32 B along K inside the swizzle span: start address field += 2
+                        ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc, (kb | kk) != 0);
                     }
                     ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs finish
-                    if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
+                    a_lo += L::kABytes >> 4;
+                    b_lo += L::kBBytes >> 4;
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                        a_lo = a_lo0;
+                        b_lo = b_lo0;
+                    }
                 }
-                __syncwarp();
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
@@ -451,20 +471,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // halo row (10 pixels = 1280 B) apart, which is the descriptor's stride-byte-offset.  The 128-byte
 // swizzle is a function of the shared-memory address (verified on B200: no descriptor base offset
 // is needed), so TMA (writer) and UMMA (reader) agree on it for any start pixel.  Layers with 32
-// input channels use the same 64-wide K block: the tensor maps end at the slice's last channel, so
-// TMA zero-fills the upper half of both operands.  Weights stream through their own, deeper pipeline (one BN x 64 tile per tap).
+// input channels use a 32-wide K block: 64-byte rows and SWIZZLE_64B for both operands (half the
+// shared-memory traffic of zero-padding K to 64 — these layers are shared-memory-bandwidth bound).
+// Weights stream through their own, deeper pipeline (one BN x BK tile per tap) or stay resident.
 constexpr int kHaloW = 10, kHaloH = 18;
-constexpr int kHaloABytes = ((kHaloW * kHaloH * 128 + 1023) / 1024) * 1024;   // 23552
+// bytes of one halo stage for a K block of BK channels (rows of 2 * BK bytes), 1024-byte aligned
+__host__ __device__ constexpr int halo_a_bytes(int bk) { return ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024; }
 
-template <int BN>
+template <int BN, int BK>
 struct HaloSmem {
-    static constexpr int kBBytes = BN * 128;
+    static constexpr int kRowBytes = BK * 2;                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    static constexpr int kABytes = halo_a_bytes(BK);
+    static constexpr int kBBytes = BN * kRowBytes;
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN>
+template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
-    using L = HaloSmem<BN>;
+    using L = HaloSmem<BN, BK>;
+    constexpr int kHaloABytes = L::kABytes;
+    constexpr int kRowBytes = L::kRowBytes;
     const int kAStages = p.a_stages, kBStages = p.stages;
     constexpr uint32_t kTmemCols = 2 * BN;
 
@@ -539,8 +565,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 ptx::mbar_wait(&aempty[sa], pa ^ 1);
                 if (ptx::elect_one()) {
-                    ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * 128);
-                    ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * 64, xb * 8 - 1,
+                    ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * kRowBytes);
+                    ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, xb * 8 - 1,
                                      yb * 16 - 1, nb);
                 }
                 __syncwarp();
@@ -550,56 +576,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     ptx::mbar_wait(&bempty[sb], pb ^ 1);
                     if (ptx::elect_one()) {
                         ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
-                        ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * 64, tap, nblk * BN);
+                        ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap, nblk * BN);
                     }
                     __syncwarp();
                     if (++sb == kBStages) { sb = 0; pb ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // MMA issuer: warp-uniform loop, one elected lane issues
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
-        const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
-        int sa = 0, sb = 0;
-        uint32_t pa = 0, pb = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int ab = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(&tempty_bar[ab], aphase ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + ab * BN;
-            for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                ptx::mbar_wait(&afull[sa], pa);
-                const uint32_t a_base = sA_u32 + sa * kHaloABytes;
-                const bool wait_b = !p.resident || tile == blockIdx.x;
-                ptx::tc_fence_after();
+    } else if (warp < kFirstEpiWarp) {
+        // MMA issuers (warps 1, 2): one elected lane each runs the whole loop for tiles it = w, w + 2, ...;
+        // descriptor low words advance by 32-bit adds (halo stage, weight stage, tap offset and K slice are all
+        // additive in the start-address field).  Ring slots: halo tile g -> g % a_stages, weight tile g -> g % b_stages.
+        const int w = warp - 1;
+        if (w < p.issuers && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+            const uint64_t a_desc0 = ptx::make_kmajor_desc_sbo<kRowBytes>(ptx::smem_u32(sA), kHaloW * kRowBytes);
+            const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
+            const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
+            const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
+            int it = w;
+            for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles;
+                 tile += p.issuers * gridDim.x, it += p.issuers) {
+                const int ab = it & 1;
+                const uint32_t d_tmem = tmem_base + ab * BN;
+                const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
+                int sa = int(ga % uint32_t(kAStages));
+                uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
+                int sb = 0;
+                uint32_t pb = 0;
+                if (!p.resident) {
+                    const uint32_t gb = ga * 9u;
+                    sb = int(gb % uint32_t(kBStages));
+                    pb = (gb / uint32_t(kBStages)) & 1u;
+                }
+                uint32_t a_lo = a_lo0 + sa * (kHaloABytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
+                // resident weights: both issuers wait once for all nine taps (phase 0 of each slot)
+                const bool wait_b = !p.resident || it < p.issuers;
+                ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    ptx::mbar_wait(&afull[sa], pa);
+                    ptx::tc_fence_after();
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    if (wait_b) {
-                        ptx::mbar_wait(&bfull[sb], pb);
-                        ptx::tc_fence_after();
-                    }
-                    if (ptx::elect_one()) {
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        const uint64_t a_desc = ptx::make_kmajor_desc_sbo(a_base + (kh * kHaloW + kw) * 128, kHaloW * 128);
-                        const uint64_t b_desc = ptx::make_kmajor_desc<128>(sB_u32 + sb * L::kBBytes);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            ptx::umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (cb | tap | kk) != 0);
-                        if (!p.resident) ptx::umma_commit(&bempty[sb]);
-                        if (tap == 8) {
-                            ptx::umma_commit(&aempty[sa]);
-                            if (cb == p.cin_blocks - 1) ptx::umma_commit(&tfull_bar[ab]);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (wait_b) {
+                            ptx::mbar_wait(&bfull[sb], pb);
+                            ptx::tc_fence_after();
                         }
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const uint32_t a_tap = a_lo + (((kh * kHaloW + kw) * kRowBytes) >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk)
+                            ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
+                                                (cb | tap | kk) != 0);
+                        if (!p.resident) ptx::umma_commit(&bempty[sb]);
+                        b_lo += L::kBBytes >> 4;
+                        if (++sb == kBStages) { sb = 0; pb ^= 1; b_lo = b_lo0; }
                     }
-                    __syncwarp();
-                    if (++sb == kBStages) { sb = 0; pb ^= 1; }
+                    ptx::umma_commit(&aempty[sa]);
+                    a_lo += kHaloABytes >> 4;
+                    if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                 }
-                if (++sa == kAStages) { sa = 0; pa ^= 1; }
+                ptx::umma_commit(&tfull_bar[ab]);
             }
         }
+        __syncwarp();
     } else {
         conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
     }
@@ -707,8 +747,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     static const int halo_env = getenv("WT_CONV_HALO") ? atoi(getenv("WT_CONV_HALO")) : 1;
     pl->halo = halo_env != 0 && halo_shape;
     if (pl->halo) {
-        bk = 64;
-        pl->bk = 64;
+        bk = d.cin % 64 == 0 ? 64 : 32;
+        pl->bk = bk;
         p.tw = 8;
         p.th = 16;
         p.tn = 1;
@@ -744,15 +784,19 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     const int fixed = fixed_smem_bytes(p.epi_bufs);
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
-        const int b_bytes = bn * 128;
+        const int b_bytes = bn * bk * 2;
+        const int kHaloABytes = halo_a_bytes(bk);
         p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
         if (p.stages > 12) p.stages = 12;
         static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
         p.resident = (resident_env && p.cin_blocks == 1 && p.n_blocks == 1 && p.stages >= 9) ? 1 : 0;
+        p.issuers = 1;
         if (p.resident) {
             p.stages = 9;   // the ring wraps once per tile: stage index == tap
             const int spare = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
-            p.a_stages = spare > kMaxAStages ? kMaxAStages : spare;
+            p.a_stages = spare >= 4 ? 4 : (spare >= 2 ? 2 : spare);
+            static const int issuers_env = getenv("WT_CONV_ISSUERS") ? atoi(getenv("WT_CONV_ISSUERS")) : 1;
+            if (p.a_stages % 2 == 0 && issuers_env == 2) p.issuers = 2;   // measured slower than one issuer: off by default   // slot s is only ever read by issuer s % 2
         }
         if (p.stages < 2) {
             delete pl;
@@ -763,6 +807,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     } else {
         p.a_stages = 0;
         p.resident = 0;
+        p.issuers = 1;
         const int stage_bytes = (kTileM + bn) * bk * 2;
         p.stages = (kSmemBudget - fixed) / stage_bytes;
         if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -795,9 +840,9 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         const uint64_t dims[3] = {uint64_t(d.cin), 9, uint64_t(d.cout)};
         const uint64_t str[2] = {uint64_t(d.cin) * 2, uint64_t(d.cin) * 2 * 9};
-        const uint32_t box[3] = {64, 1, uint32_t(bn)};
+        const uint32_t box[3] = {uint32_t(bk), 1, uint32_t(bn)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
-                          128);
+                          sw_in);
     } else {
         const uint64_t ktot = uint64_t(d.k) * d.k * d.cin;
         const uint64_t dims[2] = {ktot, uint64_t(d.cout)};
@@ -856,15 +901,15 @@ static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t
     return 0;
 }
 
-template <int BN>
+template <int BN, int BK>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBudget));
         configured = true;
     }
-    conv_halo_kernel<BN><<<grid, kThreads, smem, stream>>>(prm);
+    conv_halo_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(prm);
     WT_LAUNCHED();
     return 0;
 }
@@ -877,11 +922,19 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     if (prm.num_tiles == 0) return 0;
     const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
     if (pl->halo) {
+        if (pl->bk == 32) {   // 32 input channels (the 160x160 C2f bottlenecks)
+            switch (pl->bn) {
+                case 64: return launch_halo<64, 32>(prm, pl->smem_bytes, grid, stream);
+                case 32: return launch_halo<32, 32>(prm, pl->smem_bytes, grid, stream);
+            }
+            set_error("no halo instantiation for this (BN, 32)");
+            return 1;
+        }
         switch (pl->bn) {
-            case 256: return launch_halo<256>(prm, pl->smem_bytes, grid, stream);
-            case 128: return launch_halo<128>(prm, pl->smem_bytes, grid, stream);
-            case 64:  return launch_halo<64>(prm, pl->smem_bytes, grid, stream);
-            case 32:  return launch_halo<32>(prm, pl->smem_bytes, grid, stream);
+            case 256: return launch_halo<256, 64>(prm, pl->smem_bytes, grid, stream);
+            case 128: return launch_halo<128, 64>(prm, pl->smem_bytes, grid, stream);
+            case 64:  return launch_halo<64, 64>(prm, pl->smem_bytes, grid, stream);
+            case 32:  return launch_halo<32, 64>(prm, pl->smem_bytes, grid, stream);
         }
     }
     const int key = pl->bn * 100 + pl->bk;

@@ -210,48 +210,57 @@ __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __r
 }
 
 // ------------------------------------------------------------------ SPPF pooling chain
-// One CTA per (image, 32-channel group).  The slice lives in shared memory; each 5x5 max-pool is a
-// horizontal then a vertical 5-tap max (out-of-image taps ignored == -inf padding).
-constexpr int kPoolCg = 32;
-__global__ void __launch_bounds__(256) sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
-                                                        __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c,
-                                                        int h, int w) {
-    extern __shared__ __nv_bfloat162 pool_smem[];
+// One CTA per (image, 8-channel group): the 8 channels of a pixel are one 16-byte word, the slice
+// (h*w words) lives in shared memory, and each 5x5 max-pool is a horizontal then a vertical 5-tap max
+// (out-of-image taps ignored == -inf padding).  Small CTAs (128 threads, ~13 KB at 20x20) so that the
+// whole grid is resident at once: the kernel is a chain of six barrier-separated passes, i.e. latency-bound.
+constexpr int kPoolCg = 8;
+constexpr int kPoolThreads = 128;
+
+__device__ __forceinline__ uint4 max_bf16x8(const uint4 a, const uint4 b) {
+    uint4 r;
+    __nv_bfloat162 t;
+    t = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.x), *reinterpret_cast<const __nv_bfloat162*>(&b.x));
+    r.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.y), *reinterpret_cast<const __nv_bfloat162*>(&b.y));
+    r.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.z), *reinterpret_cast<const __nv_bfloat162*>(&b.z));
+    r.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.w), *reinterpret_cast<const __nv_bfloat162*>(&b.w));
+    r.w = *reinterpret_cast<uint32_t*>(&t);
+    return r;
+}
+
+__global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, int sct,
+                                                                 int scoff, __nv_bfloat16* __restrict__ dst, int dct,
+                                                                 int dcoff, int c, int h, int w) {
+    extern __shared__ uint4 pool_smem[];
     const int hw = h * w;
-    __nv_bfloat162* cur = pool_smem;                      // [hw][16] pairs
-    __nv_bfloat162* tmp = pool_smem + hw * (kPoolCg / 2);
+    uint4* cur = pool_smem;          // [hw]
+    uint4* tmp = pool_smem + hw;     // [hw]
     const int n = blockIdx.y;
     const int c0 = blockIdx.x * kPoolCg;
-    const int items = hw * (kPoolCg / 2);
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
-        cur[i] = *reinterpret_cast<const __nv_bfloat162*>(src + (size_t(n) * hw + pix) * sct + scoff + c0 + 2 * cp);
-    }
+    for (int i = threadIdx.x; i < hw; i += kPoolThreads)
+        cur[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t(n) * hw + i) * sct + scoff + c0));
     __syncthreads();
     for (int round = 0; round < 3; ++round) {
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {
-            const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
-            const int y = pix / w, x = pix % w;
-            __nv_bfloat162 m = cur[i];
-            for (int d = -2; d <= 2; ++d) {
-                const int xx = x + d;
-                if (d != 0 && xx >= 0 && xx < w) m = __hmax2(m, cur[(y * w + xx) * (kPoolCg / 2) + cp]);
-            }
+        for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
+            const int x = i % w;
+            uint4 m = cur[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && x + d >= 0 && x + d < w) m = max_bf16x8(m, cur[i + d]);
             tmp[i] = m;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {
-            const int pix = i / (kPoolCg / 2), cp = i % (kPoolCg / 2);
-            const int y = pix / w, x = pix % w;
-            __nv_bfloat162 m = tmp[i];
-            for (int d = -2; d <= 2; ++d) {
-                const int yy = y + d;
-                if (d != 0 && yy >= 0 && yy < h) m = __hmax2(m, tmp[(yy * w + x) * (kPoolCg / 2) + cp]);
-            }
-            *reinterpret_cast<__nv_bfloat162*>(dst + (size_t(n) * hw + pix) * dct + dcoff + round * c + c0 + 2 * cp) = m;
-            // every thread only rewrites the element it just read at index i; the next round reads
-            // neighbours, so publish after the barrier below
-            cur[i] = m;
+        for (int i = threadIdx.x; i < hw; i += kPoolThreads) {
+            const int y = i / w;
+            uint4 m = tmp[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && y + d >= 0 && y + d < h) m = max_bf16x8(m, tmp[i + d * w]);
+            *reinterpret_cast<uint4*>(dst + (size_t(n) * hw + i) * dct + dcoff + round * c + c0) = m;
+            cur[i] = m;     // only this thread touches element i before the barrier
         }
         __syncthreads();
     }
@@ -324,10 +333,11 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
 }
 
 int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream) {
-    WT_REQUIRE(c % kPoolCg == 0, "SPPF channels must be a multiple of 32");
+    WT_REQUIRE(c % kPoolCg == 0 && src.ctot % 8 == 0 && dst.ctot % 8 == 0 && src.coff % 8 == 0 && dst.coff % 8 == 0,
+               "SPPF channels and slices must be multiples of 8");
     WT_REQUIRE(src.h == dst.h && src.w == dst.w, "SPPF keeps the spatial size");
     WT_REQUIRE(src.dtype == WT_DT_BF16 && dst.dtype == WT_DT_BF16, "SPPF works on bf16");
-    const size_t smem = size_t(src.h) * src.w * kPoolCg * 2 * 2;
+    const size_t smem = size_t(src.h) * src.w * sizeof(uint4) * 2;
     WT_REQUIRE(smem <= 200 * 1024, "SPPF feature map too large for the shared-memory pool kernel");
     if (n_images == 0) return 0;
     static size_t configured = 0;
@@ -336,7 +346,7 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
         configured = smem;
     }
     dim3 grid(c / kPoolCg, n_images);
-    sppf_pool_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
+    sppf_pool_kernel<<<grid, kPoolThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
                                                   static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h,
                                                   src.w);
     WT_LAUNCHED();

@@ -141,6 +141,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with the descriptors given as (low word, high word): the high word (strides, version, swizzle)
+// is a per-kernel constant and the low word is "start address >> 4 | LBO", so stepping through taps /
+// K slices / pipeline stages is ONE 32-bit add per operand instead of rebuilding a 64-bit descriptor.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -177,14 +194,17 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     d |= layout << 61;                                       // swizzle mode, bits [61,64)
     return d;
 }
-// Same, 128-byte rows / SWIZZLE_128B, with an explicit stride between 8-row groups (halo tiles).
+// Same with an explicit stride between 8-row groups (halo tiles).
+template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle span");
+    constexpr uint64_t layout = (ROW_BYTES == 128) ? 2ull : 4ull;
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>(1) << 16;
     d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
+    d |= layout << 61;
     return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major, dense.
