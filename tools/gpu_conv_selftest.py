@@ -61,7 +61,7 @@ def main() -> int:
         arg = ",".join(str(v) for v in case)
         t0 = time.time()
         try:
-            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, timeout=90)
+            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, timeout=int(__import__("os").environ.get("WT_CASE_TIMEOUT", "40")))
             status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
             out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()
         except subprocess.TimeoutExpired:

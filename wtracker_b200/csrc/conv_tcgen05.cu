@@ -49,7 +49,7 @@ struct ConvTcParams {
     CUtensorMap tmD;      // output slice
     CUtensorMap tmR;      // residual slice (bf16)
     const float* bias;
-    int tiles_x, tiles_y, tiles_n;   // pixel-tile grid
+    int tiles_x, tiles_y, tiles_n;   // pixel-tile grid (CTA pairs: tiles_x counts PAIRS of x-adjacent tiles)
     int n_blocks;                    // cout / BN
     int tw, th, tn;                  // pixel patch, tw*th*tn == 128
     int ksize, stride;
@@ -107,14 +107,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Work item t -> (N block, pixel patch origin).  CG == 2: a work item is a PAIR of x-adjacent patches, CTA
+// `rank` of the pair takes patch 2 * xb + rank (a patch beyond the map is all TMA zero-fill / clipped stores).
+struct TileCoord {
+    int nblk, x0, y0, n0;
+};
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, int rank) {
+    TileCoord c;
+    c.nblk = t % p.n_blocks;
+    int m = t / p.n_blocks;
+    int xb = m % p.tiles_x;
+    m /= p.tiles_x;
+    const int yb = m % p.tiles_y;
+    const int nb = m / p.tiles_y;
+    if (CG == 2) xb = 2 * xb + rank;
+    c.x0 = xb * p.tw;
+    c.y0 = yb * p.th;
+    c.n0 = nb * p.tn;
+    return c;
+}
+
 // Epilogue: two groups of 4 warps; group g owns TMEM accumulator g and therefore every second tile of
 // this CTA, so the latency chain of one tile (TMEM load -> bias/SiLU/residual -> swizzled staging smem
 // -> TMA store) overlaps the chain of the next tile as well as the MMA main loop.  Thread e of a group
 // <-> accumulator row e (pixel e of the tile).  sBias holds the layer's whole bias vector.
-template <int BN>
+template <int BN, int CG>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
-                                              uint32_t tmem_base, int warp, int lane) {
+                                              uint32_t tmem_base, int warp, int lane, int rank) {
     const int g = (warp - kFirstEpiWarp) >> 2;          // epilogue group == accumulator buffer
     const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;   // 0..127 inside the group
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -131,14 +152,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
     const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
     uint32_t unit_counter = 0;
     int it = g;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
-        const int nblk = tile % p.n_blocks;
-        int m = tile / p.n_blocks;
-        const int xb = m % p.tiles_x;
-        m /= p.tiles_x;
-        const int yb = m % p.tiles_y;
-        const int nb = m / p.tiles_y;
-        const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    ptx::grid_dependency_wait();   // residual loads and output stores come after the previous kernel
+    for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
         const uint32_t aphase = (it >> 1) & 1;
         const float* bias = sBias + nblk * BN;
 
@@ -158,7 +176,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                 if (sub == BN / 32 - 1) {
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+                    if (lane == 0) {
+                        if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);   // the leader's MMA thread waits for both CTAs
+                        else ptx::mbar_arrive(&tempty_bar[g]);
+                    }
                 }
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -212,7 +233,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                 // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+                if (lane == 0) {
+                    if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);
+                    else ptx::mbar_arrive(&tempty_bar[g]);
+                }
             }
             float v[32];
 #pragma unroll
@@ -295,9 +319,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
     if (store_thread) ptx::tma_store_wait<0>();
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int CG>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-    using L = SmemLayout<BN, BK>;
+    using L = SmemLayout<BN / CG, BK>;   // a CTA of a pair holds half of the B tile (BN / 2 weight rows)
+    const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
     const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
     constexpr uint32_t kTmemCols = 2 * BN;   // double-buffered accumulator (power of two >= 64)
@@ -336,14 +362,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&tempty_bar[i], 4 * CG);   // 4 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish();
+        if (CG == 2) {
+            ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish_cg2();
+        } else {
+            ptx::tmem_alloc(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish();
+        }
     }
     // whole bias vector -> smem once per CTA
     for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
@@ -351,8 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
+    // previous kernel; the next kernel may start its own prologue now.  Activations are only touched after
+    // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
+    ptx::grid_launch_dependents();
 
     const int taps = p.ksize * p.ksize;
     const int num_kb = taps * p.cin_blocks;
@@ -361,16 +397,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         // The whole warp walks the loop (uniform control flow); one elected lane issues the copies.
+        ptx::grid_dependency_wait();
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int nblk = tile % p.n_blocks;
-            int m = tile / p.n_blocks;
-            const int xb = m % p.tiles_x;
-            m /= p.tiles_x;
-            const int yb = m % p.tiles_y;
-            const int nb = m / p.tiles_y;
-            const int x0 = xb * p.tw, y0 = yb * p.th, n0 = nb * p.tn;
+        for (int tile = first; tile < p.num_tiles; tile += step) {
+            const TileCoord tc = decode_tile<CG>(p, tile, rank);
+            const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
             for (int tap = 0; tap < taps; ++tap) {
                 const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
                 int ax, ay, mapi;
@@ -386,11 +418,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (ptx::elect_one()) {
-                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                        ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
-                                         p.src_coff + cb * BK, ax, ay, n0);
-                        ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
-                                         nblk * BN);
+                        if (CG == 2) {
+                            // both CTAs' bytes are counted on the leader's barrier; each CTA loads its own pixel
+                            // patch and its half of the weight rows
+                            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                            ptx::tma_load_4d_cg2(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                                 p.src_coff + cb * BK, ax, ay, n0);
+                            ptx::tma_load_2d_cg2(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage],
+                                                 tap * p.cin + cb * BK, nblk * BN + rank * (BN / 2));
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                            ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                             p.src_coff + cb * BK, ax, ay, n0);
+                            ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
+                                             nblk * BN);
+                        }
                     }
                     __syncwarp();
                     if (++stage == kStages) {
@@ -408,15 +450,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // Issuer w handles tiles it = w, w + 2, ...; both walk the same smem ring, whose slot for the
         // g-th K block of the CTA is g % stages.
         const int w = warp - 1;
-        if (w < p.issuers && ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+        if (w < p.issuers && rank == 0 && ptx::elect_one()) {   // CTA pairs: only the leader issues
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM * CG, BN);
             const uint64_t a_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sA));
             const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = w;
-            for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles;
-                 tile += p.issuers * gridDim.x, it += p.issuers) {
+            for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
                 const uint32_t g0 = uint32_t(it) * uint32_t(num_kb);
@@ -431,9 +472,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         // advance 16 bf16 = 32 B along K inside the swizzle span: start address field += 2
-                        ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc, (kb | kk) != 0);
+                        if (CG == 2)
+                            ptx::umma_bf16_lohi_cg2(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
+                                                    (kb | kk) != 0);
+                        else
+                            ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc, (kb | kk) != 0);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs finish
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs finish
+                    if (CG == 2) ptx::umma_commit_cg2(&empty_bar[stage]);
+                    else ptx::umma_commit(&empty_bar[stage]);
                     a_lo += L::kABytes >> 4;
                     b_lo += L::kBBytes >> 4;
                     if (++stage == kStages) {
@@ -443,20 +490,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         b_lo = b_lo0;
                     }
                 }
-                ptx::umma_commit(&tfull_bar[ab]);   // accumulator complete
+                if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);   // accumulator complete (both CTAs' epilogues)
+                else ptx::umma_commit(&tfull_bar[ab]);
             }
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
-        conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();   // nobody signals a peer barrier or reads peer smem/TMEM after this
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -478,17 +528,19 @@ constexpr int kHaloW = 10, kHaloH = 18;
 // bytes of one halo stage for a K block of BK channels (rows of 2 * BK bytes), 1024-byte aligned
 __host__ __device__ constexpr int halo_a_bytes(int bk) { return ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024; }
 
-template <int BN, int BK>
+template <int BN, int BK, int CG>
 struct HaloSmem {
     static constexpr int kRowBytes = BK * 2;                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
     static constexpr int kABytes = halo_a_bytes(BK);
-    static constexpr int kBBytes = BN * kRowBytes;
+    static constexpr int kBBytes = (BN / CG) * kRowBytes;    // a CTA of a pair holds BN / 2 weight rows
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN, int BK>
+template <int BN, int BK, int CG>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
-    using L = HaloSmem<BN, BK>;
+    using L = HaloSmem<BN, BK, CG>;
+    const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
     constexpr int kHaloABytes = L::kABytes;
     constexpr int kRowBytes = L::kRowBytes;
     const int kAStages = p.a_stages, kBStages = p.stages;
@@ -533,14 +585,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);
+            ptx::mbar_init(&tempty_bar[i], 4 * CG);   // 4 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish();
+        if (CG == 2) {
+            ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish_cg2();
+        } else {
+            ptx::tmem_alloc(tmem_slot, kTmemCols);
+            ptx::tmem_relinquish();
+        }
     }
     // whole bias vector -> smem once per CTA
     for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
@@ -548,35 +605,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
+    // previous kernel; the next kernel may start its own prologue now.  Activations are only touched after
+    // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
+    ptx::grid_launch_dependents();
 
     if (warp == 0) {
         // TMA producer: warp-uniform loop, one elected lane issues
+        ptx::grid_dependency_wait();
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int nblk = tile % p.n_blocks;
-            int m = tile / p.n_blocks;
-            const int xb = m % p.tiles_x;
-            m /= p.tiles_x;
-            const int yb = m % p.tiles_y;
-            const int nb = m / p.tiles_y;
+        for (int tile = first; tile < p.num_tiles; tile += step) {
+            const TileCoord tc = decode_tile<CG>(p, tile, rank);
+            const int nblk = tc.nblk;
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 ptx::mbar_wait(&aempty[sa], pa ^ 1);
                 if (ptx::elect_one()) {
-                    ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * kRowBytes);
-                    ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, xb * 8 - 1,
-                                     yb * 16 - 1, nb);
+                    if (CG == 2) {
+                        if (rank == 0) ptx::mbar_expect_tx(&afull[sa], 2 * kHaloW * kHaloH * kRowBytes);
+                        ptx::tma_load_4d_cg2(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
+                                             tc.x0 - 1, tc.y0 - 1, tc.n0);
+                    } else {
+                        ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * kRowBytes);
+                        ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1,
+                                         tc.y0 - 1, tc.n0);
+                    }
                 }
                 __syncwarp();
                 if (++sa == kAStages) { sa = 0; pa ^= 1; }
-                if (p.resident && tile != blockIdx.x) continue;   // weights already in shared memory
+                if (p.resident && tile != first) continue;   // weights already in shared memory
                 for (int tap = 0; tap < 9; ++tap) {
                     ptx::mbar_wait(&bempty[sb], pb ^ 1);
                     if (ptx::elect_one()) {
-                        ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
-                        ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap, nblk * BN);
+                        if (CG == 2) {
+                            if (rank == 0) ptx::mbar_expect_tx(&bfull[sb], 2 * L::kBBytes);
+                            ptx::tma_load_3d_cg2(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap,
+                                                 nblk * BN + rank * (BN / 2));
+                        } else {
+                            ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
+                            ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap, nblk * BN);
+                        }
                     }
                     __syncwarp();
                     if (++sb == kBStages) { sb = 0; pb ^= 1; }
@@ -588,15 +659,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         // descriptor low words advance by 32-bit adds (halo stage, weight stage, tap offset and K slice are all
         // additive in the start-address field).  Ring slots: halo tile g -> g % a_stages, weight tile g -> g % b_stages.
         const int w = warp - 1;
-        if (w < p.issuers && ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+        if (w < p.issuers && rank == 0 && ptx::elect_one()) {   // CTA pairs: only the leader issues
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM * CG, BN);
             const uint64_t a_desc0 = ptx::make_kmajor_desc_sbo<kRowBytes>(ptx::smem_u32(sA), kHaloW * kRowBytes);
             const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = w;
-            for (int tile = blockIdx.x + w * gridDim.x; tile < p.num_tiles;
-                 tile += p.issuers * gridDim.x, it += p.issuers) {
+            for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
                 const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
@@ -611,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 }
                 uint32_t a_lo = a_lo0 + sa * (kHaloABytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
                 // resident weights: both issuers wait once for all nine taps (phase 0 of each slot)
-                const bool wait_b = !p.resident || it < p.issuers;
+                const bool wait_b = !p.resident || it < p.issuers;   // (resident: the first tile of each issuer)
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     ptx::mbar_wait(&afull[sa], pa);
@@ -625,30 +695,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const uint32_t a_tap = a_lo + (((kh * kHaloW + kw) * kRowBytes) >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
-                                                (cb | tap | kk) != 0);
-                        if (!p.resident) ptx::umma_commit(&bempty[sb]);
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            if (CG == 2)
+                                ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
+                                                        (cb | tap | kk) != 0);
+                            else
+                                ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
+                                                    (cb | tap | kk) != 0);
+                        }
+                        if (!p.resident) {
+                            if (CG == 2) ptx::umma_commit_cg2(&bempty[sb]);
+                            else ptx::umma_commit(&bempty[sb]);
+                        }
                         b_lo += L::kBBytes >> 4;
                         if (++sb == kBStages) { sb = 0; pb ^= 1; b_lo = b_lo0; }
                     }
-                    ptx::umma_commit(&aempty[sa]);
+                    if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
+                    else ptx::umma_commit(&aempty[sa]);
                     a_lo += kHaloABytes >> 4;
                     if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                 }
-                ptx::umma_commit(&tfull_bar[ab]);
+                if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
+                else ptx::umma_commit(&tfull_bar[ab]);
             }
         }
         __syncwarp();
     } else {
-        conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane);
+        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CG == 2) ptx::cluster_sync();   // nobody signals a peer barrier or reads peer smem/TMEM after this
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -661,7 +743,8 @@ struct ConvTcPlan {
     int smem_bytes;
     bool halo;
     int bn, bk;
-    int pix_per_image_tiles;   // tiles_x * tiles_y
+    int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
+    int pix_per_image_tiles;   // tiles_x * tiles_y (work items per image and N block)
 };
 
 static void choose_patch(int w, int h, int batch, int* tw, int* th, int* tn) {
@@ -742,6 +825,12 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     ConvTcParams& p = pl->prm;
     pl->bn = bn;
     pl->bk = bk;
+    // CTA pairs (cta_group::2, M = 256, each CTA supplies half of the weight tile): implemented and parity-tested,
+    // but measured 15-30 % SLOWER than single-CTA MMAs on these layer shapes (B200, round 1), so off by default;
+    // WT_CONV_CG=2 selects it for N >= 128.
+    static const int cg_env = getenv("WT_CONV_CG") ? atoi(getenv("WT_CONV_CG")) : 1;
+    pl->cg = (cg_env == 2 && bn >= 128 && bk == 64) ? 2 : 1;
+    const int cg = pl->cg;
     // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
     // map height wastes more than a quarter of the 16-row tiles (20x20 maps stay on the generic kernel)
     static const int halo_env = getenv("WT_CONV_HALO") ? atoi(getenv("WT_CONV_HALO")) : 1;
@@ -755,7 +844,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     } else {
         choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
     }
-    p.tiles_x = ceil_div(wo, p.tw);
+    p.tiles_x = ceil_div(ceil_div(wo, p.tw), cg);   // CTA pairs: pairs of x-adjacent patches
     p.tiles_y = ceil_div(ho, p.th);
     p.tiles_n = ceil_div(d.batch, p.tn);
     p.n_blocks = d.cout / bn;
@@ -784,7 +873,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     const int fixed = fixed_smem_bytes(p.epi_bufs);
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
-        const int b_bytes = bn * bk * 2;
+        const int b_bytes = (bn / cg) * bk * 2;
         const int kHaloABytes = halo_a_bytes(bk);
         p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
         if (p.stages > 12) p.stages = 12;
@@ -808,7 +897,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         p.a_stages = 0;
         p.resident = 0;
         p.issuers = 1;
-        const int stage_bytes = (kTileM + bn) * bk * 2;
+        const int stage_bytes = (kTileM + bn / cg) * bk * 2;
         p.stages = (kSmemBudget - fixed) / stage_bytes;
         if (p.stages > kMaxStages) p.stages = kMaxStages;
         pl->smem_bytes = p.stages * stage_bytes + fixed;
@@ -840,14 +929,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         const uint64_t dims[3] = {uint64_t(d.cin), 9, uint64_t(d.cout)};
         const uint64_t str[2] = {uint64_t(d.cin) * 2, uint64_t(d.cin) * 2 * 9};
-        const uint32_t box[3] = {uint32_t(bk), 1, uint32_t(bn)};
+        const uint32_t box[3] = {uint32_t(bk), 1, uint32_t(bn / cg)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
     } else {
         const uint64_t ktot = uint64_t(d.k) * d.k * d.cin;
         const uint64_t dims[2] = {ktot, uint64_t(d.cout)};
         const uint64_t str[1] = {ktot * 2};
-        const uint32_t box[2] = {uint32_t(bk), uint32_t(bn)};
+        const uint32_t box[2] = {uint32_t(bk), uint32_t(bn / cg)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
     }
@@ -888,67 +977,95 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
 
 void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 
-template <int BN, int BK>
-static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBudget));
-        configured = true;
+template <typename Kernel>
+static int launch_kernel(Kernel kernel, bool* configured, const ConvTcParams& prm, int cg, int smem, int grid,
+                         cudaStream_t stream) {
+    if (!*configured) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        *configured = true;
     }
-    conv_tc_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(prm);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    static const int pdl_env = getenv("WT_CONV_PDL") ? atoi(getenv("WT_CONV_PDL")) : 1;
+    if (pdl_env) {   // start this kernel's prologue while the previous kernel of the stream drains
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cg > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cg;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    WT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, prm));
     WT_LAUNCHED();
     return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int CG>
+static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
+    static bool configured = false;
+    return launch_kernel(conv_tc_kernel<BN, BK, CG>, &configured, prm, CG, smem, grid, stream);
+}
+
+template <int BN, int BK, int CG>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static bool configured = false;
-    if (!configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBudget));
-        configured = true;
-    }
-    conv_halo_kernel<BN, BK><<<grid, kThreads, smem, stream>>>(prm);
-    WT_LAUNCHED();
-    return 0;
+    return launch_kernel(conv_halo_kernel<BN, BK, CG>, &configured, prm, CG, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
     ConvTcParams prm = pl->prm;
     const int tiles_n = ceil_div(n_images, prm.tn);
-    prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;
+    prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items (CTA pairs: per pair)
     prm.n_images = n_images;
     if (prm.num_tiles == 0) return 0;
-    const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+    const int cg = pl->cg;
+    const int max_ctas = sm_count / cg * cg;
+    const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
+    const int smem = pl->smem_bytes;
     if (pl->halo) {
         if (pl->bk == 32) {   // 32 input channels (the 160x160 C2f bottlenecks)
             switch (pl->bn) {
-                case 64: return launch_halo<64, 32>(prm, pl->smem_bytes, grid, stream);
-                case 32: return launch_halo<32, 32>(prm, pl->smem_bytes, grid, stream);
+                case 64: return launch_halo<64, 32, 1>(prm, smem, grid, stream);
+                case 32: return launch_halo<32, 32, 1>(prm, smem, grid, stream);
             }
             set_error("no halo instantiation for this (BN, 32)");
             return 1;
         }
-        switch (pl->bn) {
-            case 256: return launch_halo<256, 64>(prm, pl->smem_bytes, grid, stream);
-            case 128: return launch_halo<128, 64>(prm, pl->smem_bytes, grid, stream);
-            case 64:  return launch_halo<64, 64>(prm, pl->smem_bytes, grid, stream);
-            case 32:  return launch_halo<32, 64>(prm, pl->smem_bytes, grid, stream);
+        switch (pl->bn * 10 + cg) {
+            case 2562: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
+            case 1282: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
+            case 2561: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
+            case 1281: return launch_halo<128, 64, 1>(prm, smem, grid, stream);
+            case 641:  return launch_halo<64, 64, 1>(prm, smem, grid, stream);
+            case 321:  return launch_halo<32, 64, 1>(prm, smem, grid, stream);
         }
+        set_error("no halo instantiation for this (BN, CG)");
+        return 1;
     }
-    const int key = pl->bn * 100 + pl->bk;
-    switch (key) {
-        case 25664: return launch_inst<256, 64>(prm, pl->smem_bytes, grid, stream);
-        case 12864: return launch_inst<128, 64>(prm, pl->smem_bytes, grid, stream);
-        case 6464:  return launch_inst<64, 64>(prm, pl->smem_bytes, grid, stream);
-        case 3264:  return launch_inst<32, 64>(prm, pl->smem_bytes, grid, stream);
-        case 25632: return launch_inst<256, 32>(prm, pl->smem_bytes, grid, stream);
-        case 12832: return launch_inst<128, 32>(prm, pl->smem_bytes, grid, stream);
-        case 6432:  return launch_inst<64, 32>(prm, pl->smem_bytes, grid, stream);
-        case 3232:  return launch_inst<32, 32>(prm, pl->smem_bytes, grid, stream);
+    switch ((pl->bn * 100 + pl->bk) * 10 + cg) {
+        case 256642: return launch_inst<256, 64, 2>(prm, smem, grid, stream);
+        case 128642: return launch_inst<128, 64, 2>(prm, smem, grid, stream);
+        case 256641: return launch_inst<256, 64, 1>(prm, smem, grid, stream);
+        case 128641: return launch_inst<128, 64, 1>(prm, smem, grid, stream);
+        case 64641:  return launch_inst<64, 64, 1>(prm, smem, grid, stream);
+        case 32641:  return launch_inst<32, 64, 1>(prm, smem, grid, stream);
+        case 256321: return launch_inst<256, 32, 1>(prm, smem, grid, stream);
+        case 128321: return launch_inst<128, 32, 1>(prm, smem, grid, stream);
+        case 64321:  return launch_inst<64, 32, 1>(prm, smem, grid, stream);
+        case 32321:  return launch_inst<32, 32, 1>(prm, smem, grid, stream);
         default:
-            set_error("no conv_tc instantiation for this (BN, BK)");
+            set_error("no conv_tc instantiation for this (BN, BK, CG)");
             return 1;
     }
 }
