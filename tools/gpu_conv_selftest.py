@@ -10,6 +10,14 @@ import subprocess
 import sys
 import time
 
+# cases run with WT_SELFTEST_TIGHT=1 (source slice == whole buffer): the stride-2 pixel-pair halo kernel
+TIGHT_CASES = [
+    (2, 32, 32, 32, 64, 3, 2, 1, 0, 0),
+    (3, 64, 48, 32, 64, 3, 2, 1, 0, 0),      # ragged rows: 24 output rows in 16-row tiles
+    (40, 320, 320, 32, 64, 3, 2, 1, 0, 0),   # layer 1 at depth: ~54 tiles per CTA
+    (2, 64, 64, 32, 32, 3, 2, 0, 0, 0),
+]
+
 CASES = [
     # batch, h, w, cin, cout, k, stride, act, res, f32
     (2, 16, 16, 64, 64, 1, 1, 0, 0, 0),      # smallest: 1x1, no act
@@ -57,11 +65,16 @@ def main() -> int:
     if "--one" in sys.argv:
         cases = [tuple(int(v) for v in sys.argv[sys.argv.index("--one") + 1].split(","))]
     failed = 0
+    import os
+    tight = set() if "--one" in sys.argv else set(TIGHT_CASES)
+    if "--one" not in sys.argv and "--quick" not in sys.argv:
+        cases = cases + TIGHT_CASES
     for case in cases:
         arg = ",".join(str(v) for v in case)
         t0 = time.time()
+        env = dict(os.environ, WT_SELFTEST_TIGHT="1") if case in tight else None
         try:
-            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, timeout=int(__import__("os").environ.get("WT_CASE_TIMEOUT", "40")))
+            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, env=env, timeout=int(__import__("os").environ.get("WT_CASE_TIMEOUT", "40")))
             status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
             out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()
         except subprocess.TimeoutExpired:

@@ -525,20 +525,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // shared-memory traffic of zero-padding K to 64 — these layers are shared-memory-bandwidth bound).
 // Weights stream through their own, deeper pipeline (one BN x BK tile per tap) or stay resident.
 constexpr int kHaloW = 10, kHaloH = 18;
-// bytes of one halo stage for a K block of BK channels (rows of 2 * BK bytes), 1024-byte aligned
-__host__ __device__ constexpr int halo_a_bytes(int bk) { return ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024; }
+// Stride-2 form (S2 = 1, 32 input channels, e.g. layer 1): the input is viewed as PAIRS of x-adjacent pixels
+// (2 x 32 channels = one 128-byte SWIZZLE_128B row).  The tile's 33 x 9 pair-row patch is loaded once; output
+// pixel (ty, tx) at tap (kh, kw) reads input row 2*ty + kh of the patch and input x = 2*ox + kw - 1, i.e. the
+// second half of pair tx (kw = 0), the first half of pair tx + 1 (kw = 1) or its second half (kw = 2): a
+// descriptor start offset of (kh * 9 + (kw != 0)) rows + (kw != 1) * 64 bytes, 8 consecutive rows per tile row,
+// and a stride of two patch rows (18 rows) between tile rows.  One fill instead of nine strided ones.
+constexpr int kS2HaloW = 9, kS2HaloH = 33;
+// bytes of one halo stage (1024-byte aligned): S2 = 0: K block of BK channels (rows of 2 * BK bytes)
+__host__ __device__ constexpr int halo_rows(int s2) { return s2 ? kS2HaloW * kS2HaloH : kHaloW * kHaloH; }
+__host__ __device__ constexpr int halo_a_bytes(int bk, int s2) {
+    return ((halo_rows(s2) * (s2 ? 128 : bk * 2) + 1023) / 1024) * 1024;
+}
 
-template <int BN, int BK, int CG>
+template <int BN, int BK, int CG, int S2>
 struct HaloSmem {
-    static constexpr int kRowBytes = BK * 2;                 // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
-    static constexpr int kABytes = halo_a_bytes(BK);
+    static constexpr int kRowBytes = BK * 2;                 // weight rows: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    static constexpr int kARowBytes = S2 ? 128 : BK * 2;     // halo rows (S2: a pixel pair)
+    static constexpr int kABytes = halo_a_bytes(BK, S2);
+    static constexpr int kATxBytes = halo_rows(S2) * kARowBytes;
     static constexpr int kBBytes = (BN / CG) * kRowBytes;    // a CTA of a pair holds BN / 2 weight rows
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN, int BK, int CG>
+template <int BN, int BK, int CG, int S2>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
-    using L = HaloSmem<BN, BK, CG>;
+    static_assert(!S2 || (BK == 32 && CG == 1), "the stride-2 pair form is written for 32 input channels");
+    using L = HaloSmem<BN, BK, CG, S2>;
+    constexpr int kARowBytes = L::kARowBytes;
     const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
     const int first = blockIdx.x / CG, step = gridDim.x / CG;
     constexpr int kHaloABytes = L::kABytes;
@@ -625,13 +639,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 ptx::mbar_wait(&aempty[sa], pa ^ 1);
                 if (ptx::elect_one()) {
                     if (CG == 2) {
-                        if (rank == 0) ptx::mbar_expect_tx(&afull[sa], 2 * kHaloW * kHaloH * kRowBytes);
+                        if (rank == 0) ptx::mbar_expect_tx(&afull[sa], 2 * L::kATxBytes);
                         ptx::tma_load_4d_cg2(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
                                              tc.x0 - 1, tc.y0 - 1, tc.n0);
                     } else {
-                        ptx::mbar_expect_tx(&afull[sa], kHaloW * kHaloH * kRowBytes);
-                        ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1,
-                                         tc.y0 - 1, tc.n0);
+                        ptx::mbar_expect_tx(&afull[sa], L::kATxBytes);
+                        if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
+                            ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1,
+                                             tc.n0);
+                        else
+                            ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
+                                             tc.x0 - 1, tc.y0 - 1, tc.n0);
                     }
                 }
                 __syncwarp();
@@ -661,7 +679,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         const int w = warp - 1;
         if (w < p.issuers && rank == 0 && ptx::elect_one()) {   // CTA pairs: only the leader issues
             constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM * CG, BN);
-            const uint64_t a_desc0 = ptx::make_kmajor_desc_sbo<kRowBytes>(ptx::smem_u32(sA), kHaloW * kRowBytes);
+            const uint64_t a_desc0 = ptx::make_kmajor_desc_sbo<kARowBytes>(
+                ptx::smem_u32(sA), S2 ? 2 * kS2HaloW * 128 : kHaloW * kARowBytes);
             const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
@@ -693,7 +712,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             ptx::tc_fence_after();
                         }
                         const int kh = tap / 3, kw = tap - kh * 3;
-                        const uint32_t a_tap = a_lo + (((kh * kHaloW + kw) * kRowBytes) >> 4);
+                        const uint32_t a_tap =
+                            a_lo + (S2 ? (((kh * kS2HaloW + (kw != 0 ? 1 : 0)) * 128 + (kw != 1 ? 64 : 0)) >> 4)
+                                       : (((kh * kHaloW + kw) * kARowBytes) >> 4));
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             if (CG == 2)
@@ -744,6 +765,7 @@ struct ConvTcPlan {
     bool halo;
     int bn, bk;
     int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
+    int s2;                    // halo kernel in its stride-2 pixel-pair form
     int pix_per_image_tiles;   // tiles_x * tiles_y (work items per image and N block)
 };
 
@@ -791,8 +813,13 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     const int ho = d.dst.h, wo = d.dst.w;
     int sm_count = 148;
     wt_device_info(&sm_count, nullptr, nullptr);
-    const bool halo_shape = d.k == 3 && d.stride == 1 && (d.cin % 64 == 0 || d.cin == 32) && wo % 8 == 0 &&
-                            ceil_div(ho, 16) * 16 * 4 <= ho * 5;
+    static const int s2_env = getenv("WT_CONV_S2HALO") ? atoi(getenv("WT_CONV_S2HALO")) : 1;
+    const bool tall_enough = ceil_div(ho, 16) * 16 * 4 <= ho * 5;
+    // stride-2 pair form: 32 input channels that fill their buffer (a pixel pair is one contiguous 128-byte row)
+    const bool halo_s2 = s2_env && d.k == 3 && d.stride == 2 && d.cin == 32 && d.src.ctot == 32 && d.src.coff == 0 &&
+                         wo % 8 == 0 && tall_enough && d.cout % 32 == 0 && d.cout <= 64 && !d.res.base;
+    const bool halo_shape = halo_s2 || (d.k == 3 && d.stride == 1 && (d.cin % 64 == 0 || d.cin == 32) && wo % 8 == 0 &&
+                                        tall_enough);
     long long m_tiles;
     if (halo_shape) {
         m_tiles = (long long)ceil_div(wo, 8) * ceil_div(ho, 16) * d.batch;
@@ -830,6 +857,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     // WT_CONV_CG=2 selects it for N >= 128.
     static const int cg_env = getenv("WT_CONV_CG") ? atoi(getenv("WT_CONV_CG")) : 1;
     pl->cg = (cg_env == 2 && bn >= 128 && bk == 64) ? 2 : 1;
+    pl->s2 = 0;
     const int cg = pl->cg;
     // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
     // map height wastes more than a quarter of the 16-row tiles (20x20 maps stay on the generic kernel)
@@ -838,6 +866,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         bk = d.cin % 64 == 0 ? 64 : 32;
         pl->bk = bk;
+        pl->s2 = halo_s2 ? 1 : 0;
         p.tw = 8;
         p.th = 16;
         p.tn = 1;
@@ -874,7 +903,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
         const int b_bytes = (bn / cg) * bk * 2;
-        const int kHaloABytes = halo_a_bytes(bk);
+        const int kHaloABytes = halo_a_bytes(bk, pl->s2);
         p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
         if (p.stages > 12) p.stages = 12;
         static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
@@ -883,9 +912,12 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         if (p.resident) {
             p.stages = 9;   // the ring wraps once per tile: stage index == tap
             const int spare = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
-            p.a_stages = spare >= 4 ? 4 : (spare >= 2 ? 2 : spare);
+            p.a_stages = spare > kMaxAStages ? kMaxAStages : spare;
             static const int issuers_env = getenv("WT_CONV_ISSUERS") ? atoi(getenv("WT_CONV_ISSUERS")) : 1;
-            if (p.a_stages % 2 == 0 && issuers_env == 2) p.issuers = 2;   // measured slower than one issuer: off by default   // slot s is only ever read by issuer s % 2
+            if (issuers_env == 2 && p.a_stages >= 2) {
+                p.a_stages &= ~1;   // slot s is only ever read by issuer s % 2
+                p.issuers = 2;
+            }   // measured slower than one issuer: off by default   // slot s is only ever read by issuer s % 2
         }
         if (p.stages < 2) {
             delete pl;
@@ -907,7 +939,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     int rc = 0;
     const uint32_t box_a[4] = {uint32_t(bk), uint32_t(pl->halo ? kHaloW : p.tw), uint32_t(pl->halo ? kHaloH : p.th),
                                uint32_t(p.tn)};
-    if (d.stride == 1) {
+    if (pl->halo && pl->s2) {
+        // pixel-pair view of the whole input: [64 = 2 px x 32 ch][w / 2 pairs][h][n]
+        const uint64_t dims[4] = {64, uint64_t(d.src.w / 2), uint64_t(d.src.h), uint64_t(d.batch)};
+        const uint64_t str[3] = {128, uint64_t(d.src.w) * 64, uint64_t(d.src.w) * 64 * d.src.h};
+        const uint32_t box[4] = {64, kS2HaloW, kS2HaloH, 1};
+        rc |= encode_tmap(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.src.base, dims, str, box, 128);
+        for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    } else if (d.stride == 1) {
         // the channel extent ends with the slice, so a K block wider than the slice is zero-filled
         const uint64_t dims[4] = {uint64_t(d.src.coff + d.cin), uint64_t(d.src.w), uint64_t(d.src.h), uint64_t(d.batch)};
         const uint64_t str[3] = {uint64_t(d.src.ctot) * 2, uint64_t(d.src.ctot) * 2 * d.src.w,
@@ -1017,10 +1056,10 @@ static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t
     return launch_kernel(conv_tc_kernel<BN, BK, CG>, &configured, prm, CG, smem, grid, stream);
 }
 
-template <int BN, int BK, int CG>
+template <int BN, int BK, int CG, int S2 = 0>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static bool configured = false;
-    return launch_kernel(conv_halo_kernel<BN, BK, CG>, &configured, prm, CG, smem, grid, stream);
+    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2>, &configured, prm, CG, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
@@ -1034,6 +1073,14 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
     const int smem = pl->smem_bytes;
     if (pl->halo) {
+        if (pl->s2) {         // 32 -> 32/64 channels, stride 2 (layer 1)
+            switch (pl->bn) {
+                case 64: return launch_halo<64, 32, 1, 1>(prm, smem, grid, stream);
+                case 32: return launch_halo<32, 32, 1, 1>(prm, smem, grid, stream);
+            }
+            set_error("no stride-2 halo instantiation for this BN");
+            return 1;
+        }
         if (pl->bk == 32) {   // 32 input channels (the 160x160 C2f bottlenecks)
             switch (pl->bn) {
                 case 64: return launch_halo<64, 32, 1>(prm, smem, grid, stream);

@@ -216,7 +216,9 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     if (wt_device_info(&sm, &cc, nullptr)) return 1;
     const int ho = h / stride, wo = w / stride;
     // source / destination sit inside wider buffers at a channel offset to exercise slicing
-    const int src_ct = cin + 64, src_off = 32, dst_ct = cout + 64, dst_off = 32;
+    // (WT_SELFTEST_TIGHT=1: the source fills its buffer, which the stride-2 pixel-pair kernel requires)
+    const bool tight = getenv("WT_SELFTEST_TIGHT") && atoi(getenv("WT_SELFTEST_TIGHT"));
+    const int src_ct = tight ? cin : cin + 64, src_off = tight ? 0 : 32, dst_ct = cout + 64, dst_off = 32;
     const size_t n_src = size_t(batch) * h * w * src_ct, n_dst = size_t(batch) * ho * wo * dst_ct;
     const size_t n_w = size_t(cout) * k * k * cin;
     const int es = out_f32 ? 4 : 2;
