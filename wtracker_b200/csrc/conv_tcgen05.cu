@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int first = blockIdx.x / CG, step = gridDim.x / CG;
     const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
-    constexpr uint32_t kTmemCols = 2 * BN;   // double-buffered accumulator (power of two >= 64)
+    constexpr uint32_t kTmemCols = BN > 128 ? 512 : 2 * BN;   // double-buffered accumulator, a power of two >= 64
     static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
 
     // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     constexpr int kHaloABytes = L::kABytes;
     constexpr int kRowBytes = L::kRowBytes;
     const int kAStages = p.a_stages, kBStages = p.stages;
-    constexpr uint32_t kTmemCols = 2 * BN;
+    constexpr uint32_t kTmemCols = BN > 128 ? 512 : 2 * BN;   // (BN = 192: 384 columns used of 512)
 
     // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
     // starts aligned, so no slack bytes are reserved) and checked once
@@ -789,11 +789,13 @@ static void choose_patch(int w, int h, int batch, int* tw, int* th, int* tn) {
 
 // N tile: the widest one dividing cout, unless a narrower one needs fewer tile waves on this GPU (a 20x20
 // map at batch 64 is 200 pixel tiles: one 256-wide wave and a 52-tile tail cost more than three 128-wide waves).
-static int pick_bn(int cout, long long m_tiles, int sm_count) {
+static int pick_bn(int cout, long long m_tiles, int sm_count, bool allow_192) {
     int best = 0;
     long long best_cost = 0;
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-        if (cout % bn != 0) continue;
+    static const int cand[5] = {256, 192, 128, 64, 32};
+    for (int ci = 0; ci < 5; ++ci) {
+        const int bn = cand[ci];
+        if (cout % bn != 0 || (bn == 192 && !allow_192)) continue;
         const long long tiles = m_tiles * (cout / bn);
         const long long waves = (tiles + sm_count - 1) / sm_count;
         const long long cost = waves * (bn + 32);   // per-tile time ~ N plus a fixed part
@@ -828,7 +830,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         choose_patch(wo, ho, d.batch, &tw, &th, &tn);
         m_tiles = (long long)ceil_div(wo, tw) * ceil_div(ho, th) * ceil_div(d.batch, tn);
     }
-    const int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0) : pick_bn(d.cout, m_tiles, sm_count);
+    const int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0) : pick_bn(d.cout, m_tiles, sm_count, halo_shape && !halo_s2 && d.cin % 64 == 0);
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
     WT_REQUIRE(d.cout <= kMaxCout, "cout exceeds the shared-memory bias vector");
     int bk = (d.cin % 64 == 0) ? 64 : 32;
@@ -1093,6 +1095,7 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
             case 2562: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
             case 1282: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
             case 2561: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
+            case 1921: return launch_halo<192, 64, 1>(prm, smem, grid, stream);
             case 1281: return launch_halo<128, 64, 1>(prm, smem, grid, stream);
             case 641:  return launch_halo<64, 64, 1>(prm, smem, grid, stream);
             case 321:  return launch_halo<32, 64, 1>(prm, smem, grid, stream);

@@ -74,6 +74,26 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
         p.blob.extend(b.float().numpy().tobytes())
         return w_off, b_off
 
+    def add_weights_cat(parts: list[ConvSpec]) -> tuple[int, int]:
+        """Several convs over the SAME input stacked along cout (one wider conv)."""
+        ws, bs = zip(*(folded_conv(sd, s) for s in parts))
+        w_off = _align(p.blob, 16)
+        wk = torch.cat(ws, 0).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        p.blob.extend(wk.view(torch.int16).numpy().tobytes())
+        b_off = _align(p.blob, 16)
+        p.blob.extend(torch.cat(bs, 0).float().numpy().tobytes())
+        return w_off, b_off
+
+    def conv_cat(names: list[str], src: tuple[int, int], dst: tuple[int, int]):
+        parts = [specs[n] for n in names]
+        s0 = parts[0]
+        assert all((s.cin, s.k, s.stride, s.bn_act) == (s0.cin, s0.k, s0.stride, s0.bn_act) for s in parts)
+        w_off, b_off = add_weights_cat(parts)
+        p.ops.append(dict(kind=L.WT_OP_CONV, name="+".join(names), src=src[0], src_coff=src[1], dst=dst[0],
+                          dst_coff=dst[1], res=-1, res_coff=0, cin=s0.cin, cout=sum(s.cout for s in parts), k=s0.k,
+                          stride=s0.stride, act=L.WT_ACT_SILU if s0.bn_act else L.WT_ACT_NONE, w_off=w_off, b_off=b_off,
+                          dot_off=-1))
+
     def conv(name: str, src: tuple[int, int], dst: tuple[int, int], res: tuple[int, int] | None = None,
              dot: tuple[torch.Tensor, float] | None = None):
         s = specs[name]
@@ -154,19 +174,20 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
 
     # ---- head
     for lvl, (feat, down) in enumerate(((b15, 8), (b18, 16), (b21, 32))):
-        t1 = new_buf(f"head{lvl}.box1", down, arch.box_c)
+        # the first conv of the box branch and of the class branch read the same feature map: ONE conv with
+        # box_c + cls_c output channels (a wider N tile re-reads the input tile less often)
+        f1 = new_buf(f"head{lvl}.f1", down, arch.box_c + arch.cls_c)
+        t1, u1 = f1, f1
         t2 = new_buf(f"head{lvl}.box2", down, arch.box_c)
         box = new_buf(f"head{lvl}.box", down, 4 * REG_MAX, L.WT_DT_F32)
-        u1 = new_buf(f"head{lvl}.cls1", down, arch.cls_c)
         logit = new_buf(f"head{lvl}.cls", down, 1, L.WT_DT_F32)
-        conv(f"model.22.cv2.{lvl}.0", (feat, 0), (t1, 0))
+        conv_cat([f"model.22.cv2.{lvl}.0", f"model.22.cv3.{lvl}.0"], (feat, 0), (f1, 0))
         conv(f"model.22.cv2.{lvl}.1", (t1, 0), (t2, 0))
         conv(f"model.22.cv2.{lvl}.2", (t2, 0), (box, 0))
-        conv(f"model.22.cv3.{lvl}.0", (feat, 0), (u1, 0))
         # the class branch ends in a 1x1 conv with nc = 1 output: a dot product fused into the epilogue of
         # the conv before it (fp32 weights on the fp32 accumulator, the 128-channel feature map is never stored)
         wc, bc = folded_conv(sd, specs[f"model.22.cv3.{lvl}.2"])
-        conv(f"model.22.cv3.{lvl}.1", (u1, 0), (logit, 0), dot=(wc, float(bc.reshape(-1)[0])))
+        conv(f"model.22.cv3.{lvl}.1", (u1, arch.box_c), (logit, 0), dot=(wc, float(bc.reshape(-1)[0])))
         p.head.append(dict(box=box, cls_logit=logit, h=net_h // down, w=net_w // down, stride=STRIDES[lvl]))
     _align(p.blob, 16)
 
