@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 2
+#define WT_ABI_VERSION 3
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -118,7 +118,8 @@ int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op, void* stre
 /*   first-box / NaN-row logic of YoloController.predict (yolo_controller.py:80-90)            */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct wt_head_level {
-    const void* box;        /* [n][h*w][64] box-branch logits (4 sides x 16 DFL bins), box_dtype */
+    const void* box;        /* [n][h*w][64] box-branch logits (4 sides x 16 DFL bins), box_dtype; */
+                            /* or NULL when box_feat is given                                    */
     const void* cls_feat;   /* [n][h*w][cls_c] bf16 features feeding the final 1x1 cls conv, or  */
     const float* cls_logit; /* [n][h*w] f32 ready-made class logits (oracle-fed tests); one of   */
                             /* cls_feat / cls_logit is non-NULL                                  */
@@ -127,6 +128,12 @@ typedef struct wt_head_level {
     int32_t cls_c;          /* channels of cls_feat (128)                                        */
     const void* cls_w;      /* bf16 [cls_c] weight of the 1x1 cls conv (nc = 1)                  */
     float cls_b;            /* its bias                                                          */
+    /* Alternative to `box` (box == NULL): the final 1x1 conv of the box branch is evaluated ONLY  */
+    /* for the anchors that survive the confidence filter (a few per image instead of all 8400):   */
+    const void* box_feat;   /* [n][h*w][box_c] bf16 features feeding that conv                    */
+    const void* box_w;      /* bf16 [64][box_c] its weight                                        */
+    const float* box_b;     /* f32 [64] its bias                                                  */
+    int32_t box_c;          /* channels of box_feat (64), a multiple of 8                         */
 } wt_head_level;
 
 typedef struct wt_post_params {

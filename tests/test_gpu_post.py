@@ -99,3 +99,56 @@ def test_confidence_ties_resolve_to_lowest_anchor():
     got, cnt = run_post(levels, (384, 384), (360, 360), 0.1, 0.7, 1)
     want = oracle_post(levels, (384, 384), (360, 360), 0.1, 0.7, 1)
     assert cnt[0] == 1 and int(got[0, 0, 5]) == int(want[0][1][0]) == 5 * 48 + 7
+
+
+@pytest.mark.parametrize("max_det", [1, 300])
+def test_box_conv_on_survivors_equals_box_logits(max_det):
+    """wt_head_level.box_feat: the decode kernel evaluates the box branch's last 1x1 conv only for anchors that
+    pass the confidence filter.  Fed with bf16 features + bf16 weights it must keep the same anchors, in the same
+    order, as the plain path fed with the logits those features give (fp32 product of the same bf16 values)."""
+    from wtracker_b200 import _lib as L
+
+    lib = L.lib()
+    dev = torch.device("cuda:0")
+    net, img, n = (384, 384), (360, 360), 3
+    hw = [(net[0] // s, net[1] // s) for s in (8, 16, 32)]
+    g = torch.Generator().manual_seed(11)
+    keep, lv_feat, levels = [], (L.WtHeadLevel * 3)(), []
+    total = 0
+    for i, (h, w) in enumerate(hw):
+        feat = (torch.randn(n, h * w, 64, generator=g)).to(torch.bfloat16)
+        wgt = (torch.randn(64, 64, generator=g) * 0.35).to(torch.bfloat16)
+        bias = torch.randn(64, generator=g)
+        logit = torch.randn(n, h * w, generator=g) * 1.2 - 3.0
+        box = feat.float() @ wgt.float().T + bias                              # [n, hw, 64] f32
+        levels.append(torch.cat([box.permute(0, 2, 1).reshape(n, 64, h, w), logit.reshape(n, 1, h, w)], 1))
+        d = [feat.contiguous().to(dev), wgt.contiguous().to(dev), bias.to(dev), logit.contiguous().to(dev)]
+        keep += d
+        lv_feat[i] = L.WtHeadLevel(None, None, d[3].data_ptr(), h, w, (8, 16, 32)[i], L.WT_DT_F32, 0, None, 0.0,
+                                   d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), 64)
+        total += h * w
+    gain, pad_x, pad_y = Y.scale_params(net, img)
+    pp = L.WtPostParams(0.1, 0.7, max_det, net[1], net[0], img[1], img[0], gain, pad_x, pad_y)
+    out = torch.zeros((n, max_det, 6), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((n,), dtype=torch.int32, device=dev)
+    scratch = torch.zeros(lib.wt_post_scratch_bytes(n, total), dtype=torch.uint8, device=dev)
+    L.check(lib.wt_decode_nms(lv_feat, 3, n, C.byref(pp), out.data_ptr(), cnt.data_ptr(), scratch.data_ptr(), 0),
+            "wt_decode_nms")
+    torch.cuda.synchronize()
+    got, gcnt = out.cpu().numpy(), cnt.cpu().numpy()
+    ref, rcnt = run_post(levels, net, img, 0.1, 0.7, max_det)
+    assert np.array_equal(gcnt, rcnt) and gcnt.sum() > 0
+    for i in range(n):
+        assert np.array_equal(got[i, :gcnt[i], 5], ref[i, :gcnt[i], 5])
+        assert np.abs(got[i, :gcnt[i], :4] - ref[i, :gcnt[i], :4]).max() < 1e-2
+        assert np.array_equal(got[i, :gcnt[i], 4], ref[i, :gcnt[i], 4])
+
+
+def test_box_and_box_feat_are_exclusive():
+    from wtracker_b200 import _lib as L
+
+    lv = (L.WtHeadLevel * 1)(L.WtHeadLevel(None, None, None, 4, 4, 8, L.WT_DT_F32, 0, None, 0.0))
+    pp = L.WtPostParams(0.1, 0.7, 1, 32, 32, 32, 32, 1.0, 0.0, 0.0)
+    t = torch.zeros(1024, dtype=torch.uint8, device="cuda:0")
+    assert L.lib().wt_decode_nms(lv, 1, 1, C.byref(pp), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0) != 0
+    assert b"box" in L.lib().wt_last_error()

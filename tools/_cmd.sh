@@ -1,4 +1,4 @@
 export PYTHONPATH=$PWD
-bash tools/gpu_round.sh u14
-WT_CONV_PDL=0 timeout 60 python tools/gpu_layer_times.py 64 640 2>&1 | head -1
-timeout 60 python tools/gpu_layer_times.py 64 640 2>&1 | head -1
+bash tools/gpu_round.sh u17
+timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_u17.log 2>gpurun_out/bench_u17.err; tail -3 gpurun_out/bench_u17.err
+python -c "import json; d=json.loads(open('gpurun_out/bench_u17.log').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'], d['gpu_launches'])"

@@ -33,7 +33,9 @@ for name, (bid, coff, c) in eng.program.taps.items():
     err = (g - r).abs()
     print(f"{name:4s} ref std {r.std():.4f} max {r.abs().max():.3f} | abs err max {err.max():.4f} mean {err.mean():.5f} rel(mean/std) {err.mean()/r.std():.4f}")
 for lvl, h in enumerate(eng.program.head):
-    gb = eng.buffer_tensor(h["box"], n).permute(0, 3, 1, 2).cpu()
+    cb = model.model[22].cv2[lvl][2]
+    gb = (eng.buffer_tensor(h["box_feat"], n).float().cpu() @ cb.weight.view(64, -1).to(torch.bfloat16).float().T
+          + cb.bias.detach()).permute(0, 3, 1, 2)
     rb = feats[lvl][:, :64]
     e = (gb - rb).abs()
     print(f"head{lvl} box logits ref std {rb.std():.3f} | err max {e.max():.4f} mean {e.mean():.5f}")

@@ -52,6 +52,7 @@ class WtHeadLevel(C.Structure):
         ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32),
         ("box_dtype", C.c_int32), ("cls_c", C.c_int32),
         ("cls_w", C.c_void_p), ("cls_b", C.c_float),
+        ("box_feat", C.c_void_p), ("box_w", C.c_void_p), ("box_b", C.c_void_p), ("box_c", C.c_int32),
     ]
 
 
@@ -121,7 +122,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 2:
+        if handle.wt_abi_version() != 3:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

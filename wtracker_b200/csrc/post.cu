@@ -29,6 +29,7 @@ struct PostParams {
     wt_post_params pp;
     float* out_boxes;
     int32_t* out_count;
+    int box_from_feat;   // box logits are computed per surviving anchor (wt_head_level.box_feat)
     float* sc_logit;     // [n][A] class logits computed from cls_feat
     float* sc_box;       // [n][A][4] candidate boxes in sorted order (xyxy, letterboxed px)
     float* sc_conf;      // [n][A]
@@ -63,6 +64,58 @@ __device__ __forceinline__ float dfl_side(const float* lg) {
     return acc;
 }
 
+// anchor-centre distances (l, t, r, b) in stride units -> xyxy in letterboxed pixels
+__device__ __forceinline__ void box_from_sides(const wt_head_level& L, int local, float dl, float dt, float dr, float db,
+                                               float* xyxy) {
+    const float ax = float(local % L.w) + 0.5f, ay = float(local / L.w) + 0.5f;
+    const float s = float(L.stride);
+    // dist2bbox(xywh=True) * stride, then xywh2xyxy — same op order as the reference decode
+    const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+    const float cxs = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), s), cys = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), s);
+    const float ws = __fmul_rn(__fsub_rn(x2, x1), s), hs = __fmul_rn(__fsub_rn(y2, y1), s);
+    const float hw2 = __fdiv_rn(ws, 2.f), hh2 = __fdiv_rn(hs, 2.f);
+    xyxy[0] = __fsub_rn(cxs, hw2);
+    xyxy[1] = __fsub_rn(cys, hh2);
+    xyxy[2] = __fadd_rn(cxs, hw2);
+    xyxy[3] = __fadd_rn(cys, hh2);
+}
+
+// One WARP per candidate when the box logits are not materialised: the final 1x1 conv of the box branch
+// (64 outputs, box_c inputs, bf16 x bf16 products in fp32 like the tensor-core path) is evaluated for this
+// anchor only — lane o computes outputs o and o + 32 — then four lanes run the DFL expectation of one side each.
+__device__ void decode_box_from_feat(const PostParams& p, int img, int a, float* s_lg /* [64] per warp */, int lane,
+                                     float* xyxy) {
+    const int l = level_of(p, a);
+    const wt_head_level& L = p.lv[l];
+    const int local = a - p.level_start[l];
+    const __nv_bfloat16* f = static_cast<const __nv_bfloat16*>(L.box_feat) + (size_t(img) * L.h * L.w + local) * L.box_c;
+    const __nv_bfloat16* w0 = static_cast<const __nv_bfloat16*>(L.box_w) + size_t(lane) * L.box_c;
+    const __nv_bfloat16* w1 = w0 + size_t(32) * L.box_c;
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int c = 0; c < L.box_c; c += 8) {
+        const uint4 fv = __ldg(reinterpret_cast<const uint4*>(f + c));       // same address in all lanes: broadcast
+        const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(w0 + c));
+        const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(w1 + c));
+        const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w}, u0[4] = {a0.x, a0.y, a0.z, a0.w}, u1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc0 = fmaf(bf16_lo(fw[j]), bf16_lo(u0[j]), acc0);
+            acc0 = fmaf(bf16_hi(fw[j]), bf16_hi(u0[j]), acc0);
+            acc1 = fmaf(bf16_lo(fw[j]), bf16_lo(u1[j]), acc1);
+            acc1 = fmaf(bf16_hi(fw[j]), bf16_hi(u1[j]), acc1);
+        }
+    }
+    s_lg[lane] = acc0 + __ldg(L.box_b + lane);
+    s_lg[lane + 32] = acc1 + __ldg(L.box_b + lane + 32);
+    __syncwarp();
+    float side = 0.f;
+    if (lane < 4) side = dfl_side(s_lg + 16 * lane);
+    const float dl = __shfl_sync(0xffffffffu, side, 0), dt = __shfl_sync(0xffffffffu, side, 1);
+    const float dr = __shfl_sync(0xffffffffu, side, 2), db = __shfl_sync(0xffffffffu, side, 3);
+    if (lane == 0) box_from_sides(L, local, dl, dt, dr, db, xyxy);
+    __syncwarp();
+}
+
 __device__ void decode_box(const PostParams& p, int img, int a, float* xyxy) {
     const int l = level_of(p, a);
     const wt_head_level& L = p.lv[l];
@@ -90,17 +143,7 @@ __device__ void decode_box(const PostParams& p, int img, int a, float* xyxy) {
         }
     }
     const float dl = dfl_side(lg), dt = dfl_side(lg + 16), dr = dfl_side(lg + 32), db = dfl_side(lg + 48);
-    const float ax = float(local % L.w) + 0.5f, ay = float(local / L.w) + 0.5f;
-    const float s = float(L.stride);
-    // dist2bbox(xywh=True) * stride, then xywh2xyxy — same op order as the reference decode
-    const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt), x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
-    const float cxs = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), s), cys = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), s);
-    const float ws = __fmul_rn(__fsub_rn(x2, x1), s), hs = __fmul_rn(__fsub_rn(y2, y1), s);
-    const float hw2 = __fdiv_rn(ws, 2.f), hh2 = __fdiv_rn(hs, 2.f);
-    xyxy[0] = __fsub_rn(cxs, hw2);
-    xyxy[1] = __fsub_rn(cys, hh2);
-    xyxy[2] = __fadd_rn(cxs, hw2);
-    xyxy[3] = __fadd_rn(cys, hh2);
+    box_from_sides(L, local, dl, dt, dr, db, xyxy);
 }
 
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
@@ -155,6 +198,7 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     __shared__ float4 s_keep[kMaxKeep];
     __shared__ int s_keep_src[kMaxKeep];
     __shared__ int s_nkeep;
+    __shared__ float s_lg[kPostThreads / 32][64];   // box logits of the candidate a warp is decoding
 
     const int img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -227,14 +271,28 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     }
 
     // ---- (c) decode candidates in sorted order
-    for (int i = tid; i < n_sorted; i += kPostThreads) {
-        const unsigned long long k = keys[i];
-        const int a = int(0xFFFFFFFFu - unsigned(k & 0xFFFFFFFFull));
-        float b[4];
-        decode_box(p, img, a, b);
-        cbox[4 * i] = b[0]; cbox[4 * i + 1] = b[1]; cbox[4 * i + 2] = b[2]; cbox[4 * i + 3] = b[3];
-        cconf[i] = __uint_as_float(unsigned(k >> 32));
-        cidx[i] = a;
+    if (p.box_from_feat) {
+        for (int i = warp; i < n_sorted; i += kPostThreads / 32) {       // one warp per candidate
+            const unsigned long long k = keys[i];
+            const int a = int(0xFFFFFFFFu - unsigned(k & 0xFFFFFFFFull));
+            float b[4] = {0.f, 0.f, 0.f, 0.f};
+            decode_box_from_feat(p, img, a, s_lg[warp], lane, b);
+            if (lane == 0) {
+                cbox[4 * i] = b[0]; cbox[4 * i + 1] = b[1]; cbox[4 * i + 2] = b[2]; cbox[4 * i + 3] = b[3];
+                cconf[i] = __uint_as_float(unsigned(k >> 32));
+                cidx[i] = a;
+            }
+        }
+    } else {
+        for (int i = tid; i < n_sorted; i += kPostThreads) {
+            const unsigned long long k = keys[i];
+            const int a = int(0xFFFFFFFFu - unsigned(k & 0xFFFFFFFFull));
+            float b[4];
+            decode_box(p, img, a, b);
+            cbox[4 * i] = b[0]; cbox[4 * i + 1] = b[1]; cbox[4 * i + 2] = b[2]; cbox[4 * i + 3] = b[3];
+            cconf[i] = __uint_as_float(unsigned(k >> 32));
+            cidx[i] = a;
+        }
     }
     __syncthreads();
 
@@ -331,13 +389,18 @@ extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, c
         p.lv[l] = levels[l];
         p.level_start[l] = total;
         total += levels[l].h * levels[l].w;
-        WT_REQUIRE(levels[l].box, "box logits missing");
+        WT_REQUIRE((levels[l].box != nullptr) != (levels[l].box_feat != nullptr), "give box or box_feat");
+        if (levels[l].box_feat)
+            WT_REQUIRE(levels[l].box_c % 8 == 0 && levels[l].box_c >= 8 && levels[l].box_w && levels[l].box_b,
+                       "box feature channels / weights");
+        WT_REQUIRE((levels[l].box_feat != nullptr) == (levels[0].box_feat != nullptr), "all levels give box or all give box_feat");
         WT_REQUIRE((levels[l].cls_feat != nullptr) != (levels[l].cls_logit != nullptr), "give cls_feat or cls_logit");
         if (levels[l].cls_feat)
             WT_REQUIRE(levels[l].cls_c % 8 == 0 && levels[l].cls_c <= kMaxClsC && levels[l].cls_w, "cls feature channels");
     }
     for (int l = n_levels; l <= kMaxLevels; ++l) p.level_start[l] = total;
     p.n_levels = n_levels;
+    p.box_from_feat = levels[0].box_feat != nullptr;
     p.total_anchors = total;
     int cap = 1;
     while (cap < total) cap <<= 1;

@@ -73,8 +73,10 @@ class DetectorEngine:
                                        device=self.device)
             levels = (L.WtHeadLevel * 3)()
             for i, h in enumerate(self.program.head):
-                levels[i] = L.WtHeadLevel(self.buffer_ptr(h["box"]), None, self.buffer_ptr(h["cls_logit"]), h["h"],
-                                          h["w"], h["stride"], L.WT_DT_F32, 0, None, 0.0)
+                levels[i] = L.WtHeadLevel(None, None, self.buffer_ptr(h["cls_logit"]), h["h"], h["w"], h["stride"],
+                                          L.WT_DT_F32, 0, None, 0.0, self.buffer_ptr(h["box_feat"]),
+                                          self.weights.data_ptr() + h["box_w_off"],
+                                          self.weights.data_ptr() + h["box_b_off"], h["box_c"])
             self._levels = levels
             pad_x, pad_y = self.lb.scale_pad
             self._post = L.WtPostParams(self.conf, self.iou, self.max_det, self.lb.dst_w, self.lb.dst_h,

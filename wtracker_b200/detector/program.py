@@ -10,7 +10,8 @@ Layout decisions:
     for the UMMA B operand), biases fp32;
   * the first conv sees three identical grey channels scaled by 1/255, so its weights are summed
     over the input channels and divided by 255 on the host and it runs on the u8 image directly;
-  * the last 1x1 of the box branch writes fp32 (DFL is sensitive to logit rounding); the last 1x1
+  * the last 1x1 of the box branch is evaluated in fp32 by the decode kernel, only for anchors that pass
+    the confidence filter; the last 1x1
     of the class branch (cout = nc = 1) is a dot product fused into the epilogue of the 3x3 conv
     before it (wt_op.dot_off), which then writes one fp32 logit per anchor.
 """
@@ -179,16 +180,22 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
         f1 = new_buf(f"head{lvl}.f1", down, arch.box_c + arch.cls_c)
         t1, u1 = f1, f1
         t2 = new_buf(f"head{lvl}.box2", down, arch.box_c)
-        box = new_buf(f"head{lvl}.box", down, 4 * REG_MAX, L.WT_DT_F32)
         logit = new_buf(f"head{lvl}.cls", down, 1, L.WT_DT_F32)
         conv_cat([f"model.22.cv2.{lvl}.0", f"model.22.cv3.{lvl}.0"], (feat, 0), (f1, 0))
         conv(f"model.22.cv2.{lvl}.1", (t1, 0), (t2, 0))
-        conv(f"model.22.cv2.{lvl}.2", (t2, 0), (box, 0))
+        # the last 1x1 of the box branch (64 DFL logits per anchor) is NOT run over the map: the decode kernel
+        # evaluates it for the few anchors that pass the confidence filter (wt_head_level.box_feat)
+        wb, bb = folded_conv(sd, specs[f"model.22.cv2.{lvl}.2"])
+        bw_off = _align(p.blob, 16)
+        p.blob.extend(wb.reshape(wb.shape[0], -1).to(torch.bfloat16).contiguous().view(torch.int16).numpy().tobytes())
+        bb_off = _align(p.blob, 16)
+        p.blob.extend(bb.float().numpy().tobytes())
         # the class branch ends in a 1x1 conv with nc = 1 output: a dot product fused into the epilogue of
         # the conv before it (fp32 weights on the fp32 accumulator, the 128-channel feature map is never stored)
         wc, bc = folded_conv(sd, specs[f"model.22.cv3.{lvl}.2"])
         conv(f"model.22.cv3.{lvl}.1", (u1, arch.box_c), (logit, 0), dot=(wc, float(bc.reshape(-1)[0])))
-        p.head.append(dict(box=box, cls_logit=logit, h=net_h // down, w=net_w // down, stride=STRIDES[lvl]))
+        p.head.append(dict(box_feat=t2, box_w_off=bw_off, box_b_off=bb_off, box_c=arch.box_c, cls_logit=logit,
+                           h=net_h // down, w=net_w // down, stride=STRIDES[lvl]))
     _align(p.blob, 16)
 
     p.taps = {
