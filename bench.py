@@ -317,8 +317,15 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
         per_op = np.median(per_op, axis=0)
         conv_ms = float(sum(t for t, o in zip(per_op, ops) if o["kind"] == L.WT_OP_CONV))
         conv_launches = sum(1 for o in ops if o["kind"] == L.WT_OP_CONV)
-        conv0_flops = 2 * (IMGSZ // 2) ** 2 * arch.c[0] * 27     # layer 0 runs on CUDA cores, not in the tcgen05 kernel
-        conv_flops = (flops_per_frame - conv0_flops) * B
+        # FLOPs the tcgen05 kernels actually execute (2*M*N*K per conv op of the program, + the fused class-logit dot
+        # product): layer 0 runs on CUDA cores, and the box branch's last 1x1 convs run only for surviving anchors
+        # inside the decode kernel, so neither is credited here.
+        conv_flops = 0
+        for o in ops:
+            if o["kind"] == L.WT_OP_CONV:
+                h, w = hp.det.program.bufs[o["dst"]][:2]
+                conv_flops += 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 + (2 * h * w * o["cout"] if o.get("dot_off", -1) >= 0 else 0)
+        conv_flops *= B
 
     if rank != 0:
         return None
@@ -355,7 +362,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
         "gather_ms": gather_ms,
         "detected_fraction": detected,
         "roofline": {
-            "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all 62 launches of one step)",
+            "kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit-GEMM conv, every conv launch of one step)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
             "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": conv_launches,

@@ -42,6 +42,25 @@ extern std::atomic<uint64_t> g_launch_count;        // kernels launched by this 
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may start (up to its
+// griddepcontrol.wait) while the previous kernel of the stream drains.  The kernel MUST execute
+// griddepcontrol.wait before touching memory written by earlier kernels.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Encodes a tiled tensor map (rank <= 5). dims/box in elements (innermost first), strides in bytes
 // for dims 1..rank-1. swizzle_bytes in {0, 32, 64, 128}. Returns 0 on success.
 int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* base, const uint64_t* dims,

@@ -3,6 +3,7 @@
 // only to validate the tcgen05 kernel (tests / WT conv_impl=1).
 #include "../../include/wtracker_b200.h"
 #include "conv.cuh"
+#include "ptx.cuh"
 
 namespace wt {
 
@@ -110,16 +111,23 @@ __device__ __forceinline__ Conv0Raw conv0_load_row(const uint8_t* __restrict__ i
     return r;
 }
 
+// u8 -> f32 without the conversion pipe: byte k of v placed in the mantissa of 2^23 (one PRMT), minus 2^23
+// (one FADD).  I2F runs on the 16-lane XU pipe shared with MUFU, which bounded this kernel.
+template <int K>
+__device__ __forceinline__ float byte_to_float(uint32_t v) {
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | K)) - 8388608.0f;
+}
+
 __device__ __forceinline__ void conv0_unpack(const Conv0Raw& r, float (&in)[9]) {
-    in[0] = float(r.left);
-    in[1] = float(r.v.x & 0xFFu);
-    in[2] = float((r.v.x >> 8) & 0xFFu);
-    in[3] = float((r.v.x >> 16) & 0xFFu);
-    in[4] = float(r.v.x >> 24);
-    in[5] = float(r.v.y & 0xFFu);
-    in[6] = float((r.v.y >> 8) & 0xFFu);
-    in[7] = float((r.v.y >> 16) & 0xFFu);
-    in[8] = float(r.v.y >> 24);
+    in[0] = byte_to_float<0>(r.left);
+    in[1] = byte_to_float<0>(r.v.x);
+    in[2] = byte_to_float<1>(r.v.x);
+    in[3] = byte_to_float<2>(r.v.x);
+    in[4] = byte_to_float<3>(r.v.x);
+    in[5] = byte_to_float<0>(r.v.y);
+    in[6] = byte_to_float<1>(r.v.y);
+    in[7] = byte_to_float<2>(r.v.y);
+    in[8] = byte_to_float<3>(r.v.y);
 }
 
 template <int COUT>
@@ -144,10 +152,8 @@ __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __r
     const int y_end = min(y_begin + kConv0Rows, ho);
     const uint8_t* img = src + size_t(n) * h * w;
 
-    // the first three input rows are in flight while the weights load
-    Conv0Raw raw0 = conv0_load_row(img, w, h, 2 * y_begin - 1, x0);
-    Conv0Raw raw1 = conv0_load_row(img, w, h, 2 * y_begin, x0);
-    Conv0Raw raw2 = conv0_load_row(img, w, h, 2 * y_begin + 1, x0);
+    // weights are constants: loaded while the previous kernel (the crop / letterbox) may still be draining
+    ptx::grid_launch_dependents();
     float wreg[9][8], breg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -155,6 +161,10 @@ __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __r
 #pragma unroll
         for (int t = 0; t < 9; ++t) wreg[t][j] = __ldg(w9 + (g * 8 + j) * 9 + t);
     }
+    ptx::grid_dependency_wait();
+    Conv0Raw raw0 = conv0_load_row(img, w, h, 2 * y_begin - 1, x0);
+    Conv0Raw raw1 = conv0_load_row(img, w, h, 2 * y_begin, x0);
+    Conv0Raw raw2 = conv0_load_row(img, w, h, 2 * y_begin + 1, x0);
     float r0[9], r1[9], r2[9];          // input rows 2y-1, 2y, 2y+1
     conv0_unpack(raw0, r0);
     for (int y = y_begin; y < y_end; ++y) {
@@ -240,6 +250,8 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(const __nv_bflo
     uint4* tmp = pool_smem + hw;     // [hw]
     const int n = blockIdx.y;
     const int c0 = blockIdx.x * kPoolCg;
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     for (int i = threadIdx.x; i < hw; i += kPoolThreads)
         cur[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t(n) * hw + i) * sct + scoff + c0));
     __syncthreads();
@@ -270,6 +282,8 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(const __nv_bflo
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sct, int scoff,
                                   __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c8, long long total) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     if (idx >= total) return;
     const int g = int(idx % c8);
     long long pix = idx / c8;
@@ -322,12 +336,9 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
     const int threads = kConv0Threads;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dst.base);
-    if (cout == 32)
-        conv0_kernel<32><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
-    else if (cout == 16)
-        conv0_kernel<16><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
-    else
-        conv0_kernel<64><<<blocks, threads, 0, stream>>>(src, h, w, w9, bias, act, out, dst.ctot, dst.coff, total);
+    auto* kernel = cout == 32 ? conv0_kernel<32> : (cout == 16 ? conv0_kernel<16> : conv0_kernel<64>);
+    WT_CHECK_CUDA(launch_pdl(kernel, dim3(blocks), dim3(threads), 0, stream, src, h, w, w9, bias, act, out, dst.ctot,
+                             dst.coff, total));
     WT_LAUNCHED();
     return 0;
 }
@@ -346,9 +357,9 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
         configured = smem;
     }
     dim3 grid(c / kPoolCg, n_images);
-    sppf_pool_kernel<<<grid, kPoolThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
-                                                  static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h,
-                                                  src.w);
+    WT_CHECK_CUDA(launch_pdl(sppf_pool_kernel, grid, dim3(kPoolThreads), smem, stream,
+                             static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
+                             static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w));
     WT_LAUNCHED();
     return 0;
 }
@@ -360,9 +371,9 @@ int upsample2x_launch(const TensorView& src, const TensorView& dst, int c, int n
     const long long total = (long long)n_images * dst.h * dst.w * (c / 8);
     if (total == 0) return 0;
     const int threads = 256;
-    upsample2x_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(src.base), src.h, src.w, src.ctot, src.coff,
-        static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c / 8, total);
+    WT_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, stream,
+                             static_cast<const __nv_bfloat16*>(src.base), src.h, src.w, src.ctot, src.coff,
+                             static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c / 8, total));
     WT_LAUNCHED();
     return 0;
 }
