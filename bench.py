@@ -84,7 +84,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -167,6 +167,18 @@ class CpuReference:
         return time.perf_counter() - t0
 
 
+def workload_config(batch: int, world: int) -> dict:
+    """The `config` object both arms print (BASELINE.json configs[1])."""
+    return {
+        "workload": "YOLOv8s (nc=1) 640x640 bf16 batched detect+predict: crop(1080x1920 u8) -> YOLOv8s -> DFL/NMS "
+                    "(conf 0.1, iou 0.7, max_det 1) -> ResMLP-100ms -> bbox error",
+        "batch_per_gpu": batch, "global_batch": batch * world, "imgsz": IMGSZ, "view": VIEW, "frame": "1080x1920 u8",
+        "weights": "seeded synthetic yolov8s (nc=1, fp16-rounded) + committed ResMLP(imaging-100ms) checkpoint",
+        "parallelism": f"frame-range sharding x{world}, one final gather",
+        "l2": "no flush needed: per-step activation working set ~4 GB >> 126 MB L2, inputs differ every step",
+    }
+
+
 def run_reference(args, rank: int) -> dict | None:
     if rank != 0:
         return None
@@ -177,13 +189,14 @@ def run_reference(args, rank: int) -> dict | None:
     times = [ref.step((args.warmup + s) * sample, sample) for s in range(args.steps)]
     total = sum(times)
     fps = sample * args.steps / total
-    desc = f"{sample} of {args.batch} frames per step (same synthetic frames / crop schedule), torch {ref.torch.__version__} CPU fp32"
+    desc = (f"{sample} of the {args.batch} frames of a step per timed step (same synthetic frames / crop schedule); oracle port "
+            f"of the reference algorithm (torch {ref.torch.__version__} CPU fp32 YOLOv8s + numpy pre/post/ResMLP/metrics), "
+            f"{ref.cores} threads")
     return {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLOv8s 640x640 batched detect+predict, oracle port of the reference algorithm on host CPUs",
-                   "batch": sample, "imgsz": IMGSZ, "view": VIEW, "weights": "seeded synthetic yolov8s (nc=1) + committed ResMLP-100ms"},
+        "config": workload_config(args.batch, args.gpus),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ref.cores, "kind": "port", "sample": desc},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -252,7 +265,6 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = L.launch_count() - launches0
-    clock_info = clocks.stop() if clocks else None
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -295,6 +307,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert n_out == K * B
+    clock_info = clocks.stop() if clocks else None     # sampled every 50 ms over the device-timed AND the e2e-timed loops
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -339,19 +352,19 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None        # DRAM bytes of one step's conv launches from the committed ncu --set full capture
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        if t.get("batch") == B and t.get("imgsz") == IMGSZ:
+            traffic = t["dram_bytes_per_step"]
+    except (OSError, ValueError, KeyError):
+        pass
 
     out = {
         "metric": METRIC, "value": world * B * K / (elapsed_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {
-            "workload": "YOLOv8s (nc=1) 640x640 bf16 batched detect+predict: crop(1080x1920 u8) -> YOLOv8s -> DFL/NMS "
-                        "(conf 0.1, iou 0.7, max_det 1) -> ResMLP-100ms -> bbox error",
-            "batch_per_gpu": B, "global_batch": B * world, "imgsz": IMGSZ, "view": VIEW, "frame": "1080x1920 u8",
-            "weights": "seeded synthetic yolov8s (nc=1, fp16-rounded) + committed ResMLP(imaging-100ms) checkpoint",
-            "parallelism": f"frame-range sharding x{world}, one final gather",
-            "l2": "no flush needed: per-step activation working set ~4 GB >> 126 MB L2, inputs differ every step",
-        },
+        "config": workload_config(B, world),
         "e2e": {"value": world * B * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": hp.h2d_bytes_per_step,
                 "d2h_bytes_per_step": hp.d2h_bytes_per_step,
                 "api": "HotPath.run_host(iterator of pinned u8 view batches) -> host result arrays per batch (3-stream pipeline: H2D | detect | rows+ResMLP+D2H)"},
@@ -364,7 +377,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
         "roofline": {
             "kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit-GEMM conv, every conv launch of one step)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
             "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": conv_launches,
             "share_of_step": conv_ms / (elapsed_ms / K), "peak_source": peak_src,
         },

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 3
+#define WT_ABI_VERSION 4
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -95,6 +95,12 @@ typedef struct wt_op {
                                  /* class-logit conv of the head, nc = 1): the activated output */
                                  /* is not stored; dst (f32, c = 1) receives                    */
                                  /* sum_c out[c] * w[c] + b per pixel.  Needs cout <= 256.      */
+    int32_t add_buf, add_coff;   /* CONV only, add_buf = -1: none.  Otherwise an f32 buffer of HALF the  */
+                                 /* destination's spatial size whose channels [add_coff, add_coff+cout) */
+                                 /* are added, nearest-2x-upsampled, to the accumulator BEFORE the      */
+                                 /* activation.  A 1x1 conv over concat(upsample2x(a), b) is split by    */
+                                 /* linearity into conv_a(a) at half resolution (this addend, bias       */
+                                 /* included) + conv_b(b): the upsampled tensor is never materialised.   */
 } wt_op;
 
 typedef struct wt_engine wt_engine;

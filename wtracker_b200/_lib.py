@@ -43,6 +43,7 @@ class WtOp(C.Structure):
         ("k", C.c_int32), ("stride", C.c_int32),
         ("act", C.c_int32),
         ("w_off", C.c_int64), ("b_off", C.c_int64), ("dot_off", C.c_int64),
+        ("add_buf", C.c_int32), ("add_coff", C.c_int32),
     ]
 
 
@@ -122,7 +123,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 3:
+        if handle.wt_abi_version() != 4:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

@@ -15,6 +15,7 @@ struct TensorView {      // NHWC view of (a channel slice of) an activation buff
 
 struct ConvDesc {
     TensorView src, dst, res;   // res.base == nullptr -> no residual
+    TensorView add;             // add.base == nullptr -> none; else f32 half-resolution pre-activation addend (wt_op.add_buf)
     int cin, cout, k, stride, act;
     const __nv_bfloat16* w;     // [cout][k][k][cin]
     const float* bias;          // [cout]

@@ -58,6 +58,10 @@ struct ConvTcParams {
     int src_coff, dst_coff, res_coff;
     int act, has_res, out_f32;
     int num_tiles;
+    // half-resolution f32 pre-activation addend (wt_op.add_buf): per tile the spare warp 2 TMA-loads the
+    // (tw/2 x th/2 x tn)-pixel patch of the addend map into shared memory, one buffer per epilogue group
+    CUtensorMap tmP;
+    int has_add, add_coff;
     // fused 1-channel 1x1 head (wt_op.dot_off): out pixel = sum_c act(conv)[c] * dot_w[c] + dot_w[cout]
     const float* dot_w;
     float* dot_out;                  // f32 [n][out_h][out_w]
@@ -89,6 +93,9 @@ struct SmemLayout {
 __host__ __device__ constexpr int fixed_smem_bytes(int epi_bufs) {
     return kEpiGroups * epi_bufs * kStageBufBytes + kMaxCout * 4 + kBarrierBytes;
 }
+// addend patches between the staging buffers and the bias vector (generic kernel only): per epilogue group
+// 32 low-res pixels x BN f32
+__host__ __device__ constexpr int add_smem_bytes(int bn) { return kEpiGroups * bn * 128; }
 
 // SiLU(v) = v * sigmoid(v) = h * tanh(h) + h with h = v / 2: ONE MUFU op (tanh.approx) per element
 // instead of two (ex2 + rcp) — the epilogue warps are MUFU/issue bound, not the tensor pipe.  Measured on
@@ -135,7 +142,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
 template <int BN, int CG>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
-                                              uint32_t tmem_base, int warp, int lane, int rank) {
+                                              uint32_t tmem_base, int warp, int lane, int rank,
+                                              const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
+                                              uint64_t* add_empty = nullptr) {
     const int g = (warp - kFirstEpiWarp) >> 2;          // epilogue group == accumulator buffer
     const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;   // 0..127 inside the group
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -159,6 +168,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
         const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
         const uint32_t aphase = (it >> 1) & 1;
         const float* bias = sBias + nblk * BN;
+
+        // Upsampled addend (wt_op.add_buf): warp 2 has TMA-loaded this tile's half-resolution patch into this group's
+        // buffer as [BN / 32 slices][32 low-res pixels][32 f32] with the 128-byte swizzle; this thread's pixel
+        // (lx, ly, ln) of the (tw, th, tn) patch reads low-res pixel (lx / 2, ly / 2, ln).
+        const uint8_t* add_row = nullptr;
+        int add_xr = 0;
+        if (p.has_add) {
+            const int lx = row % p.tw, ly = (row / p.tw) % p.th, ln = row / (p.tw * p.th);
+            const int prow = (ln * (p.th >> 1) + (ly >> 1)) * (p.tw >> 1) + (lx >> 1);
+            add_row = sAddAll + g * (BN * 128) + prow * 128;
+            add_xr = prow & 7;
+            ptx::mbar_wait(&add_full[g], aphase);
+        }
 
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
@@ -246,6 +268,20 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                 v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
                 v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
                 v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
+            }
+            if (p.has_add) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 a = *reinterpret_cast<const float4*>(add_row + sub * 4096 + ((j4 ^ add_xr) << 4));
+                    v[4 * j4 + 0] += a.x;
+                    v[4 * j4 + 1] += a.y;
+                    v[4 * j4 + 2] += a.z;
+                    v[4 * j4 + 3] += a.w;
+                }
+                if (sub == BN / 32 - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&add_empty[g]);
+                }
             }
             if (p.act == WT_ACT_SILU) {
                 // v * sigmoid(v) with ex2.approx + rcp.approx (2 MUFU): relative error ~1e-6 everywhere.
@@ -337,14 +373,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint8_t* sA = smem;                                  // [stages][128][BK] bf16 (swizzled)
     uint8_t* sB = smem + kStages * L::kABytes;           // [stages][BN][BK]  bf16 (swizzled)
     uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 groups x epi_bufs x 16 KB epilogue staging
-    float* sBias = reinterpret_cast<float*>(sStage + kEpiGroups * p.epi_bufs * kStageBufBytes);   // [kMaxCout]
+    // addend patches [2 groups][BN / 32][32 px][128 B], 1024-byte aligned like everything before them (128-byte swizzle)
+    const uint8_t* sAdd = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;
+    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sAdd) + (p.has_add ? add_smem_bytes(BN) : 0));   // [kMaxCout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
     uint64_t* full_bar = bars;                          // [stages]  TMA -> MMA
     uint64_t* empty_bar = bars + kMaxStages;            // [stages]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]       MMA -> epilogue group
     uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;   // [2]       epilogue group -> MMA
     uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2][2]    residual TMA -> epilogue group
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 8);
+    uint64_t* add_full = bars + 2 * kMaxStages + 8;     // [2]       addend patch TMA -> epilogue group
+    uint64_t* add_empty = bars + 2 * kMaxStages + 10;   // [2]       epilogue group -> addend loader
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 12);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -365,6 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             ptx::mbar_init(&tempty_bar[i], 4 * CG);   // 4 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&add_full[i], 1);
+            ptx::mbar_init(&add_empty[i], 4);
+        }
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -389,6 +433,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // previous kernel; the next kernel may start its own prologue now.  Activations are only touched after
     // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
     ptx::grid_launch_dependents();
+
+    if (warp == 2 && p.has_add) {
+        // ------------------------------------------------------------------ addend loader (the spare issuer warp)
+        // tile it -> epilogue group it & 1; the group's buffer is refilled as soon as its four warps released it
+        if (ptx::elect_one()) {
+            ptx::prefetch_tmap(&p.tmP);
+            ptx::grid_dependency_wait();
+            int it = 0;
+            for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+                const int g = it & 1;
+                const TileCoord tc = decode_tile<CG>(p, tile, rank);
+                ptx::mbar_wait(&add_empty[g], ((it >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(&add_full[g], BN * 128);
+                for (int sub = 0; sub < BN / 32; ++sub)
+                    ptx::tma_load_4d(const_cast<uint8_t*>(sAdd) + g * (BN * 128) + sub * 4096, &p.tmP, &add_full[g],
+                                     p.add_coff + tc.nblk * BN + sub * 32, tc.x0 >> 1, tc.y0 >> 1, tc.n0);
+            }
+        }
+        __syncwarp();
+    }
 
     const int taps = p.ksize * p.ksize;
     const int num_kb = taps * p.cin_blocks;
@@ -497,7 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
-        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank);
+        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, sAdd,
+                              add_full, add_empty);
     }
 
     ptx::tc_fence_before();
@@ -830,7 +895,9 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         choose_patch(wo, ho, d.batch, &tw, &th, &tn);
         m_tiles = (long long)ceil_div(wo, tw) * ceil_div(ho, th) * ceil_div(d.batch, tn);
     }
-    const int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0) : pick_bn(d.cout, m_tiles, sm_count, halo_shape && !halo_s2 && d.cin % 64 == 0);
+    int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0)
+                     : pick_bn(d.cout, m_tiles, sm_count, halo_shape && !halo_s2 && d.cin % 64 == 0);
+    if (d.add.base && bn > 128) bn = 128;   // the addend patch buffers (N x 128 B per epilogue group) stay small
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
     WT_REQUIRE(d.cout <= kMaxCout, "cout exceeds the shared-memory bias vector");
     int bk = (d.cin % 64 == 0) ? 64 : 32;
@@ -842,6 +909,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     }
     const bool out_f32 = d.dst.dtype == WT_DT_F32;
     WT_REQUIRE(!(out_f32 && d.res.base), "residual only with bf16 output");
+    WT_REQUIRE(!(d.add.base && d.dot_w), "addend and dot head are not combined");
+    WT_REQUIRE(!d.add.base || (d.k == 1 && d.stride == 1), "the upsampled addend is implemented for 1x1 convs");
     if (d.dot_w) {
         WT_REQUIRE(bn == d.cout && 2 * d.cout + 1 <= kMaxCout, "a dot-head conv needs all channels in one N tile");
         WT_REQUIRE(out_f32 && d.dst.ctot == 1 && !d.res.base, "a dot-head conv writes a 1-channel f32 buffer");
@@ -892,6 +961,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.has_res = d.res.base ? 1 : 0;
     p.out_f32 = out_f32 ? 1 : 0;
     p.bias = d.bias;
+    p.has_add = d.add.base ? 1 : 0;
+    p.add_coff = d.add.coff;
     p.dot_w = d.dot_w;
     p.dot_out = d.dot_w ? static_cast<float*>(d.dst.base) : nullptr;
     p.out_w = wo;
@@ -901,7 +972,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     // shared-memory plan
     p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
-    const int fixed = fixed_smem_bytes(p.epi_bufs);
+    const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0);
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
         const int b_bytes = (bn / cg) * bk * 2;
@@ -980,6 +1051,20 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const uint32_t box[2] = {uint32_t(bk), uint32_t(bn / cg)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
+    }
+    p.tmP = p.tmA[0];
+    if (d.add.base) {
+        if (pl->halo || pl->cg != 1 || p.tw < 2 || p.th < 2 || d.add.h * 2 != ho || d.add.w * 2 != wo) {
+            set_error("the upsampled addend needs the generic single-CTA kernel and an even pixel patch");
+            rc = 1;
+        } else {
+            // f32 [n][h/2][w/2][ctot]; one box = 32 channels (128 B) of the (tw/2 x th/2 x tn) low-resolution patch
+            const uint64_t dims[4] = {uint64_t(d.add.ctot), uint64_t(d.add.w), uint64_t(d.add.h), uint64_t(d.batch)};
+            const uint64_t str[3] = {uint64_t(d.add.ctot) * 4, uint64_t(d.add.ctot) * 4 * d.add.w,
+                                     uint64_t(d.add.ctot) * 4 * d.add.w * d.add.h};
+            const uint32_t box[4] = {32, uint32_t(p.tw / 2), uint32_t(p.th / 2), uint32_t(p.tn)};
+            rc |= encode_tmap(&p.tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.add.base, dims, str, box, 128);
+        }
     }
     if (d.dot_w) {
         p.tmD = p.tmA[0];   // never used: the dot head stores with plain st.global

@@ -106,6 +106,15 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             d.dst = view_of(e, o.dst, o.dst_coff);
             if (o.res >= 0) d.res = view_of(e, o.res, o.res_coff);
             else d.res = TensorView{nullptr, 0, 0, 0, 0, 0};
+            d.add = TensorView{nullptr, 0, 0, 0, 0, 0};
+            if (o.add_buf >= 0) {
+                if (o.add_buf >= n_bufs) return fail("addend buffer id out of range", i);
+                const wt_buf& ab = e->bufs[o.add_buf];
+                if (ab.dtype != WT_DT_F32 || ab.h * 2 != e->bufs[o.dst].h || ab.w * 2 != e->bufs[o.dst].w ||
+                    o.add_coff < 0 || o.add_coff + o.cout > ab.c || o.add_coff % 4 != 0 || ab.c % 4 != 0)
+                    return fail("the upsampled addend must be an f32 buffer of half the destination size", i);
+                d.add = view_of(e, o.add_buf, o.add_coff);
+            }
             d.cin = o.cin;
             d.cout = o.cout;
             d.k = o.k;
@@ -243,6 +252,7 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     d.src = TensorView{d_src, h, w, src_ct, src_off, WT_DT_BF16};
     d.dst = TensorView{d_out_tc, ho, wo, dst_ct, dst_off, out_f32 ? WT_DT_F32 : WT_DT_BF16};
     d.res = with_residual ? TensorView{d_res, ho, wo, dst_ct, dst_off, WT_DT_BF16} : TensorView{nullptr, 0, 0, 0, 0, 0};
+    d.add = TensorView{nullptr, 0, 0, 0, 0, 0};
     d.cin = cin; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
     d.w = d_w; d.bias = d_bias; d.dot_w = nullptr; d.batch = batch;
     ConvTcPlan* plan = nullptr;

@@ -21,7 +21,8 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, 
                                  void* __restrict__ dst, int dh, int dw, int dct, int dcoff, int dst_f32,
                                  const __nv_bfloat16* __restrict__ res, int rct, int rcoff,
                                  const __nv_bfloat16* __restrict__ wgt, const float* __restrict__ bias, int cin,
-                                 int cout, int k, int stride, int act, long long total) {
+                                 int cout, int k, int stride, int act, const float* __restrict__ add, int act_ct,
+                                 int acoff, long long total) {
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int co = int(idx % cout);
@@ -44,6 +45,7 @@ __global__ void conv_simt_kernel(const __nv_bfloat16* __restrict__ src, int sh, 
         }
     }
     float v = acc + bias[co];
+    if (add) v += add[((size_t(n) * (dh / 2) + (y >> 1)) * (dw / 2) + (x >> 1)) * act_ct + acoff + co];
     if (act == WT_ACT_SILU) v = silu_f(v);
     const size_t opix = (size_t(n) * dh + y) * dw + x;
     if (res) v += __bfloat162float(res[opix * rct + rcoff + co]);
@@ -319,7 +321,7 @@ int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream) {
         static_cast<const __nv_bfloat16*>(d.src.base), d.src.h, d.src.w, d.src.ctot, d.src.coff, d.dst.base, d.dst.h,
         d.dst.w, d.dst.ctot, d.dst.coff, d.dst.dtype == WT_DT_F32 ? 1 : 0,
         static_cast<const __nv_bfloat16*>(d.res.base), d.res.ctot, d.res.coff, d.w, d.bias, d.cin, d.cout, d.k,
-        d.stride, d.act, total);
+        d.stride, d.act, static_cast<const float*>(d.add.base), d.add.ctot, d.add.coff, total);
     WT_LAUNCHED();
     return 0;
 }

@@ -4,6 +4,8 @@
 Layout decisions:
   * activations are NHWC bf16; every Concat of the network is a *buffer*: producers store straight
     into their channel slice (TMA store with a channel offset), so concatenation costs nothing;
+  * the two nearest-2x upsamples of the neck and the concats after them are not executed: the 1x1 conv that
+    consumes concat(upsample(a), b) is evaluated as upsample(conv_a(a)) + conv_b(b) (wt_op.add_buf);
   * C2f: one buffer of (2+n)*c channels holds cv1's two halves and every bottleneck output; the
     bottlenecks read/write channel slices of it, cv2 reads it whole;
   * BatchNorm is folded into the conv weights; weights are bf16 [cout][kh][kw][cin] (K-major rows
@@ -95,6 +97,35 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
                           stride=s0.stride, act=L.WT_ACT_SILU if s0.bn_act else L.WT_ACT_NONE, w_off=w_off, b_off=b_off,
                           dot_off=-1))
 
+    def add_weights_slice(s: ConvSpec, c_lo: int, c_hi: int, with_bias: bool) -> tuple[int, int]:
+        """Input-channel slice [c_lo, c_hi) of a conv (one term of a conv over a concatenation)."""
+        w, b = folded_conv(sd, s)
+        w_off = _align(p.blob, 16)
+        wk = w[:, c_lo:c_hi].permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        p.blob.extend(wk.view(torch.int16).numpy().tobytes())
+        b_off = _align(p.blob, 16)
+        p.blob.extend((b if with_bias else torch.zeros_like(b)).float().numpy().tobytes())
+        return w_off, b_off
+
+    def conv_over_upsampled_cat(name: str, low: tuple[int, int], c_low: int, high: tuple[int, int], c_high: int,
+                                dst: tuple[int, int], down: int):
+        """``name`` is a 1x1 conv over concat(upsample2x(low), high).  By linearity it equals
+        act(upsample2x(W_low * low + b) + W_high * high): the first term is a 1x1 conv at HALF resolution written
+        as f32 (no activation), the second adds it, nearest-upsampled, before its activation (wt_op.add_buf).
+        Neither the upsampled tensor nor the concatenation is ever written."""
+        s = specs[name]
+        assert s.k == 1 and s.stride == 1 and s.cin == c_low + c_high
+        part = new_buf(f"{name}.low", down * 2, s.cout, L.WT_DT_F32)
+        w_off, b_off = add_weights_slice(s, 0, c_low, with_bias=True)
+        p.ops.append(dict(kind=L.WT_OP_CONV, name=name + "[low]", src=low[0], src_coff=low[1], dst=part, dst_coff=0,
+                          res=-1, res_coff=0, cin=c_low, cout=s.cout, k=1, stride=1, act=L.WT_ACT_NONE, w_off=w_off,
+                          b_off=b_off, dot_off=-1, add_buf=-1, add_coff=0))
+        w_off, b_off = add_weights_slice(s, c_low, c_low + c_high, with_bias=False)
+        p.ops.append(dict(kind=L.WT_OP_CONV, name=name + "[high]", src=high[0], src_coff=high[1], dst=dst[0],
+                          dst_coff=dst[1], res=-1, res_coff=0, cin=c_high, cout=s.cout, k=1, stride=1,
+                          act=L.WT_ACT_SILU if s.bn_act else L.WT_ACT_NONE, w_off=w_off, b_off=b_off, dot_off=-1,
+                          add_buf=part, add_coff=0))
+
     def conv(name: str, src: tuple[int, int], dst: tuple[int, int], res: tuple[int, int] | None = None,
              dot: tuple[torch.Tensor, float] | None = None):
         s = specs[name]
@@ -108,12 +139,18 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
                           cout=s.cout, k=s.k, stride=s.stride, act=L.WT_ACT_SILU if s.bn_act else L.WT_ACT_NONE,
                           w_off=w_off, b_off=b_off, dot_off=dot_off))
 
-    def c2f(idx: int, src: tuple[int, int], dst: tuple[int, int], down: int):
+    def c2f(idx: int, src, dst: tuple[int, int], down: int):
+        """``src`` is (buffer, channel offset) or, for the two neck blocks fed by concat(upsample(a), b),
+        a dict(low=(buf, coff), c_low=.., high=(buf, coff), c_high=..)."""
         spec = arch.c2f[idx]
         cc = spec.c
         cat = new_buf(f"c2f{idx}.cat", down, (2 + spec.n) * cc)
         tmp = new_buf(f"c2f{idx}.tmp", down, cc)
-        conv(f"model.{idx}.cv1", src, (cat, 0))
+        if isinstance(src, dict):
+            conv_over_upsampled_cat(f"model.{idx}.cv1", src["low"], src["c_low"], src["high"], src["c_high"], (cat, 0),
+                                    down)
+        else:
+            conv(f"model.{idx}.cv1", src, (cat, 0))
         for i in range(spec.n):
             x_in = (cat, (1 + i) * cc)
             conv(f"model.{idx}.m.{i}.cv1", x_in, (tmp, 0))
@@ -126,9 +163,9 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     b1 = new_buf("m1", 4, c[1])
     b2 = new_buf("m2", 4, c[1])
     b3 = new_buf("m3", 8, c[2])
-    cat14 = new_buf("cat14", 8, c[3] + c[2])      # [up(x12) | x4]
+    b4 = new_buf("m4", 8, c[2])                   # x4  (concat(up(x12), x4) is never materialised)
     b5 = new_buf("m5", 16, c[3])
-    cat11 = new_buf("cat11", 16, c[4] + c[3])     # [up(x9)  | x6]
+    b6 = new_buf("m6", 16, c[3])                  # x6  (concat(up(x9), x6) is never materialised)
     b7 = new_buf("m7", 32, c[4])
     b8 = new_buf("m8", 32, c[4])
     sppf = new_buf("sppf.cat", 32, 2 * c[4])      # [cv1 | pool5 | pool9 | pool13]
@@ -149,25 +186,20 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     conv("model.1", (b0, 0), (b1, 0))
     c2f(2, (b1, 0), (b2, 0), 4)
     conv("model.3", (b2, 0), (b3, 0))
-    c2f(4, (b3, 0), (cat14, c[3]), 8)             # x4
-    conv("model.5", (cat14, c[3]), (b5, 0))
-    c2f(6, (b5, 0), (cat11, c[4]), 16)            # x6
-    conv("model.7", (cat11, c[4]), (b7, 0))
+    c2f(4, (b3, 0), (b4, 0), 8)                   # x4
+    conv("model.5", (b4, 0), (b5, 0))
+    c2f(6, (b5, 0), (b6, 0), 16)                  # x6
+    conv("model.7", (b6, 0), (b7, 0))
     c2f(8, (b7, 0), (b8, 0), 32)
     conv("model.9.cv1", (b8, 0), (sppf, 0))
     p.ops.append(dict(kind=L.WT_OP_SPPF_POOL, name="model.9.m", src=sppf, src_coff=0, dst=sppf, dst_coff=c[4] // 2,
                       res=-1, res_coff=0, cin=c[4] // 2, cout=c[4] // 2, k=5, stride=1, act=0, w_off=0, b_off=0))
     conv("model.9.cv2", (sppf, 0), (cat20, c[3]))  # x9
 
-    # ---- neck
-    def upsample(name, src, dst, ch):
-        p.ops.append(dict(kind=L.WT_OP_UPSAMPLE2X, name=name, src=src[0], src_coff=src[1], dst=dst[0], dst_coff=dst[1],
-                          res=-1, res_coff=0, cin=ch, cout=ch, k=1, stride=1, act=0, w_off=0, b_off=0))
-
-    upsample("model.10", (cat20, c[3]), (cat11, 0), c[4])
-    c2f(12, (cat11, 0), (cat17, c[2]), 16)        # x12
-    upsample("model.13", (cat17, c[2]), (cat14, 0), c[3])
-    c2f(15, (cat14, 0), (b15, 0), 8)              # x15
+    # ---- neck.  model.10 / model.13 (nearest 2x upsample) and model.11 / model.14 (concat) do not exist as ops:
+    # the 1x1 conv that consumes concat(upsample(a), b) is split by linearity (conv_over_upsampled_cat)
+    c2f(12, dict(low=(cat20, c[3]), c_low=c[4], high=(b6, 0), c_high=c[3]), (cat17, c[2]), 16)        # x12
+    c2f(15, dict(low=(cat17, c[2]), c_low=c[3], high=(b4, 0), c_high=c[2]), (b15, 0), 8)              # x15
     conv("model.16", (b15, 0), (cat17, 0))
     c2f(18, (cat17, 0), (b18, 0), 16)             # x18
     conv("model.19", (b18, 0), (cat20, 0))
@@ -199,7 +231,7 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     _align(p.blob, 16)
 
     p.taps = {
-        "x4": (cat14, c[3], c[2]), "x6": (cat11, c[4], c[3]), "x9": (cat20, c[3], c[4]),
+        "x4": (b4, 0, c[2]), "x6": (b6, 0, c[3]), "x9": (cat20, c[3], c[4]),
         "x12": (cat17, c[2], c[3]), "x15": (b15, 0, c[2]), "x18": (b18, 0, c[3]), "x21": (b21, 0, c[4]),
         "m0": (b0, 0, c[0]), "m1": (b1, 0, c[1]), "m2": (b2, 0, c[1]), "m3": (b3, 0, c[2]),
     }
@@ -211,7 +243,7 @@ def ops_as_ctypes(p: Program):
     ops = (L.WtOp * len(p.ops))()
     for i, o in enumerate(p.ops):
         ops[i] = L.WtOp(o["kind"], o["src"], o["src_coff"], o["dst"], o["dst_coff"], o["res"], o["res_coff"],
-                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1))
+                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1), o.get("add_buf", -1), o.get("add_coff", 0))
     return bufs, ops
 
 
