@@ -81,3 +81,19 @@ def test_metrics_large_and_properties():
     assert np.array_equal(ErrorCalculator.calculate_mse_error(worm, worm)[np.isfinite(worm).all(1)], np.zeros(int(np.isfinite(worm).all(1).sum())))
     assert np.array_equal(ErrorCalculator.calculate_mse_error(worm, mic), metrics_ref.mse_error(worm, mic), equal_nan=True)
     assert ErrorCalculator.calculate_bbox_error(np.zeros((0, 4)), np.zeros((0, 4))).shape == (0,)
+
+
+@pytest.mark.parametrize("path", [RESMLP_100, RESMLP_200])
+def test_resmlp_small_and_large_batch_kernels_agree_bitwise(path):
+    """n <= 2048 runs one warp per sample, larger batches one thread per sample; both accumulate each neuron in the
+    same order, so the same rows must give the same bits."""
+    from wtracker_b200.neural.engine import ResMLPEngine
+    from wtracker_b200.neural.mlp import load_worm_predictor
+
+    eng = ResMLPEngine(load_worm_predictor(path))
+    d = eng.shape["in_dim"]
+    x = (torch.randn(4096, d, generator=torch.Generator().manual_seed(5)) * 6).cuda()
+    big = eng.forward(x)                 # thread-per-sample kernel
+    small = eng.forward(x[:2048].contiguous())       # warp-per-sample kernel
+    one = eng.forward(x[77:78].contiguous())
+    assert torch.equal(big[:2048], small) and torch.equal(big[77:78], one)
