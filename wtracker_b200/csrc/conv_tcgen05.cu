@@ -750,6 +750,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = w;
+            if (kBStages == 9) {
+                // Weight ring of exactly nine slots (resident weights, or the host chose 9 stages): slot == tap, so
+                // every weight descriptor and barrier address in the unrolled tap loop is base + immediate and the
+                // ring bookkeeping disappears from the issue loop (the issuing thread, not the tensor pipe, bounds
+                // narrow-N layers).  Slot parity of channel block g of the CTA: g & 1.
+                for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
+                    const int ab = it & 1;
+                    const uint32_t d_tmem = tmem_base + ab * BN;
+                    const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
+                    int sa = int(ga % uint32_t(kAStages));
+                    uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
+                    uint32_t a_lo = a_lo0 + sa * (kHaloABytes >> 4);
+                    const bool wait_b = !p.resident || it < p.issuers;
+                    ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
+                    for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                        const uint32_t pb = (ga + cb) & 1u;
+                        ptx::mbar_wait(&afull[sa], pa);
+                        ptx::tc_fence_after();
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            if (wait_b) {
+                                ptx::mbar_wait(&bfull[tap], pb);
+                                ptx::tc_fence_after();
+                            }
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            const uint32_t a_tap =
+                                a_lo + (S2 ? (((kh * kS2HaloW + (kw != 0 ? 1 : 0)) * 128 + (kw != 1 ? 64 : 0)) >> 4)
+                                           : (((kh * kHaloW + kw) * kARowBytes) >> 4));
+                            const uint32_t b_tap = b_lo0 + tap * (L::kBBytes >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; ++kk) {
+                                if (CG == 2)
+                                    ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
+                                                            (cb | tap | kk) != 0);
+                                else
+                                    ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
+                                                        (cb | tap | kk) != 0);
+                            }
+                            if (!p.resident) {
+                                if (CG == 2) ptx::umma_commit_cg2(&bempty[tap]);
+                                else ptx::umma_commit(&bempty[tap]);
+                            }
+                        }
+                        if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
+                        else ptx::umma_commit(&aempty[sa]);
+                        a_lo += kHaloABytes >> 4;
+                        if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
+                    }
+                    if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
+                    else ptx::umma_commit(&tfull_bar[ab]);
+                }
+            } else
             for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
@@ -979,6 +1031,13 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const int kHaloABytes = halo_a_bytes(bk, pl->s2);
         p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
         if (p.stages > 12) p.stages = 12;
+        // exactly nine weight slots (slot == tap: the fast issue loop) if they fit beside two halo stages
+        static const int nine_env = getenv("WT_CONV_NINE") ? atoi(getenv("WT_CONV_NINE")) : 1;
+        if (nine_env && p.stages != 9 && 9 * b_bytes + 2 * kHaloABytes + fixed <= kSmemBudget) {
+            p.stages = 9;
+            p.a_stages = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
+            if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
+        }
         static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
         p.resident = (resident_env && p.cin_blocks == 1 && p.n_blocks == 1 && p.stages >= 9) ? 1 : 0;
         p.issuers = 1;
