@@ -23,7 +23,7 @@ for r in rows[2:]:
         return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(un, 1.0)
     rd, wr = mb("dram__bytes_read.sum"), mb("dram__bytes_write.sum")
     tot_us += us; tot_rd += rd; tot_wr += wr
-    print(f"{r[col['ID']]:>3} {name[:42]:42s} {int(g(r,'launch__grid_size')):5d} {us:8.1f} {rd:9.1f} {wr:9.1f} {(rd+wr)/us*1e-6 if us else 0:9.2f} "
+    print(f"{r[col['ID']]:>3} {name[:42]:42s} {int(g(r,'launch__grid_size')):5d} {us:8.1f} {rd:9.1f} {wr:9.1f} {(rd+wr)/us if us else 0:9.2f} "
           f"{g(r,'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):8.1f} {g(r,'lts__throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} "
           f"{g(r,'lts__t_sector_hit_rate.pct'):7.1f} {int(g(r,'launch__registers_per_thread')):5d}")
 print(f"# total: {len(rows) - 2} launches, {tot_us:.1f} us, DRAM read {tot_rd:.1f} MB + write {tot_wr:.1f} MB = {tot_rd + tot_wr:.1f} MB")
