@@ -1,4 +1,7 @@
 export PYTHONPATH=$PWD
-bash tools/gpu_round.sh u22
-timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_u22.log 2>gpurun_out/bench_u22.err; tail -3 gpurun_out/bench_u22.err
-python -c "import json; d=json.loads(open('gpurun_out/bench_u22.log').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['stage_ms'], d['roofline']['achieved'], d['gpu_launches'], d['clocks'])"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 200 python bench.py > gpurun_out/bench_default.log 2>gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
+python -c "
+import json; d=json.loads(open('gpurun_out/bench_default.log').read().strip().splitlines()[-1])
+print({k: d[k] for k in ('value','ms_per_step','gpu_launches','clocks','cpu_baseline')})
+print(d['e2e']); print(d['roofline'])"
