@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kEpiGroups = 2;           // epilogue warp groups; group g drains TMEM accumulator g (tiles it % 2 == g)
-constexpr int kEpiThreads = 128;        // threads per epilogue group (4 warps = the 4 TMEM lane quadrants)
+constexpr int kEpiThreads = 256;        // threads per epilogue group (8 warps = 4 TMEM lane quadrants x 2 column halves)
 constexpr int kMmaWarps = 2;            // MMA issuer warps; issuer w owns accumulator w (tiles it % 2 == w)
 constexpr int kFirstEpiWarp = 1 + kMmaWarps;
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiGroups * kEpiThreads;
@@ -135,18 +135,96 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
     return c;
 }
 
-// Epilogue: two groups of 4 warps; group g owns TMEM accumulator g and therefore every second tile of
-// this CTA, so the latency chain of one tile (TMEM load -> bias/SiLU/residual -> swizzled staging smem
-// -> TMA store) overlaps the chain of the next tile as well as the MMA main loop.  Thread e of a group
-// <-> accumulator row e (pixel e of the tile).  sBias holds the layer's whole bias vector.
+// Epilogue: two groups of 8 warps; group g owns TMEM accumulator g and therefore every second tile of this
+// CTA, so the latency chain of one tile (TMEM load -> bias/SiLU/residual -> swizzled staging smem -> TMA
+// store) overlaps the chain of the next tile as well as the MMA main loop.  Inside a group, warp pair
+// (q, h) drains TMEM lane quadrant q (accumulator rows 32q..32q+31 = 32 pixels of the tile) and column
+// half h of every staging unit: the epilogue is latency bound (ncu, round 1: 17 % issue utilisation with
+// one warp per quadrant, 'wait' the top stall, every 1x1 / narrow-N layer limited by it and not by HBM or
+// the tensor pipe), so each accumulator row is split over two threads.  sBias holds the layer's whole bias
+// vector, pre-multiplied by 1/2 for the tanh form of SiLU (h = acc/2 + bias/2 is one FFMA).
+
+// Fused class-logit head (wt_op.dot_off): thread (row, h) sums its half of the pixel's channels, the halves meet
+// in shared memory.
 template <int BN, int CG>
-__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
-                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
-                                              uint32_t tmem_base, int warp, int lane, int rank,
-                                              const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
-                                              uint64_t* add_empty = nullptr) {
-    const int g = (warp - kFirstEpiWarp) >> 2;          // epilogue group == accumulator buffer
-    const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;   // 0..127 inside the group
+__device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
+                                                  uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                                  int warp, int lane, int rank) {
+    const int ew = warp - kFirstEpiWarp;
+    const int g = ew >> 3, h = (ew >> 2) & 1;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* part = reinterpret_cast<float*>(sStageAll + g * p.epi_bufs * kStageBufBytes);   // [2 slots][128]
+    const float* dw = sBias + p.cout;
+    const int bar_id = kEpiBarrier + g;
+    int it = g;
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    ptx::grid_dependency_wait();
+    for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tfull_bar[g], aphase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + h * (BN / 2);
+        const float* bias = sBias + h * (BN / 2);
+        const float* dwh = dw + h * (BN / 2);
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {   // 16 columns per step, BN / 2 columns per thread
+            uint32_t acc[16];
+            ptx::tmem_ld_32x16(t_row + c * 16, acc);
+            ptx::tmem_ld_wait();
+            if (c == BN / 32 - 1) {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);   // the leader's MMA thread waits for both CTAs
+                    else ptx::mbar_arrive(&tempty_bar[g]);
+                }
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + c * 16 + 4 * j4);
+                const float4 w = *reinterpret_cast<const float4*>(dwh + c * 16 + 4 * j4);
+                const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float v;
+                    if (p.act == kActSiluTanh) {
+                        const float hh = fmaf(__uint_as_float(acc[4 * j4 + e]), 0.5f, bb[e]);
+                        v = fmaf(hh, tanh_fast(hh), hh);
+                    } else {
+                        v = __uint_as_float(acc[4 * j4 + e]) + bb[e];
+                        if (p.act == WT_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
+                    }
+                    dot = fmaf(v, ww[e], dot);
+                }
+            }
+        }
+        float* slot = part + aphase * kTileM;
+        if (h == 1) slot[row] = dot;
+        ptx::bar_sync(bar_id, kEpiThreads);   // (the slot is rewritten two tiles of this group later: one more barrier in between)
+        if (h == 0) {
+            const int px = tc.x0 + row % p.tw;
+            const int py = tc.y0 + (row / p.tw) % p.th;
+            const int pn = tc.n0 + row / (p.tw * p.th);
+            if (px < p.out_w && py < p.out_h && pn < p.n_images)
+                p.dot_out[(size_t(pn) * p.out_h + py) * p.out_w + px] = (dot + slot[row]) + dw[p.cout];
+        }
+    }
+}
+
+// CW = accumulator columns per thread and staging unit: 32 (bf16 output, units of 64 channels = 128-byte staging
+// rows) or 16 (f32 output: units of 32 channels = 128-byte rows; bf16 with BN == 32: one unit of 64-byte rows).
+template <int BN, int CG, int CW>
+__device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
+                                                 uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
+                                                 uint32_t tmem_base, int warp, int lane, int rank,
+                                                 const uint8_t* sAddAll, uint64_t* add_full, uint64_t* add_empty) {
+    const int ew = warp - kFirstEpiWarp;
+    const int g = ew >> 3;                  // epilogue group == accumulator buffer
+    const int h = (ew >> 2) & 1;            // column half of every unit
+    const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;   // 0..255 inside the group
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;          // accumulator row == pixel index inside the tile
     const bool store_thread = (et == 0);
@@ -154,10 +232,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
     uint8_t* sStage = sStageAll + g * p.epi_bufs * kStageBufBytes;
     uint64_t* res_bar = res_bar_all + 2 * g;
     const int bar_id = kEpiBarrier + g;
-    // bf16 output: a staging row holds 64 channels (32 when BN == 32); f32 output: 32 channels
-    const int subs_per_unit = p.out_f32 ? 1 : (BN == 32 ? 1 : 2);
-    const int unit_ch = p.out_f32 ? 32 : (BN == 32 ? 32 : 64);
-    const bool rows64 = (!p.out_f32) && (BN == 32);   // 64-byte staging rows (SWIZZLE_64B)
+    constexpr int kUnitCh = 2 * CW;                       // channels per staging unit
+    constexpr int kUnits = BN / kUnitCh;
+    const bool rows64 = CW == 16 && !p.out_f32;           // bf16, BN == 32: 64-byte staging rows (SWIZZLE_64B)
     const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
     uint32_t unit_counter = 0;
     int it = g;
@@ -167,7 +244,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
         const TileCoord tc = decode_tile<CG>(p, tile, rank);
         const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
         const uint32_t aphase = (it >> 1) & 1;
-        const float* bias = sBias + nblk * BN;
+        const float* bias = sBias + nblk * BN + h * CW;
 
         // Upsampled addend (wt_op.add_buf): warp 2 has TMA-loaded this tile's half-resolution patch into this group's
         // buffer as [BN / 32 slices][32 low-res pixels][32 f32] with the 128-byte swizzle; this thread's pixel
@@ -184,75 +261,27 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
 
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN;
-
-        if (p.dot_w) {
-            // fused class-logit head: this thread owns one pixel and all its output channels (n_blocks == 1)
-            const float* dw = sBias + p.cout;
-            float dot = 0.f;
-#pragma unroll 1
-            for (int sub = 0; sub < BN / 32; ++sub) {
-                uint32_t acc[32];
-                ptx::tmem_ld_32x32(t_row + sub * 32, acc);
-                ptx::tmem_ld_wait();
-                if (sub == BN / 32 - 1) {
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);   // the leader's MMA thread waits for both CTAs
-                        else ptx::mbar_arrive(&tempty_bar[g]);
-                    }
-                }
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias + sub * 32 + 4 * j4);
-                    const float4 w = *reinterpret_cast<const float4*>(dw + sub * 32 + 4 * j4);
-                    const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float v = __uint_as_float(acc[4 * j4 + e]) + bb[e];
-                        if (p.act == WT_ACT_SILU) {
-                            v = __fdividef(v, 1.0f + __expf(-v));
-                        } else if (p.act == kActSiluTanh) {
-                            const float h = 0.5f * v;
-                            v = fmaf(h, tanh_fast(h), h);
-                        }
-                        dot = fmaf(v, ww[e], dot);
-                    }
-                }
-            }
-            const int px = x0 + row % p.tw;
-            const int py = y0 + (row / p.tw) % p.th;
-            const int pn = n0 + row / (p.tw * p.th);
-            if (px < p.out_w && py < p.out_h && pn < p.n_images)
-                p.dot_out[(size_t(pn) * p.out_h + py) * p.out_w + px] = dot + dw[p.cout];
-            continue;
-        }
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + h * CW;
 
 #pragma unroll 1
-        for (int sub = 0; sub < BN / 32; ++sub) {
-            const int sub_in_unit = sub % subs_per_unit;
-            const int unit = sub / subs_per_unit;
+        for (int unit = 0; unit < kUnits; ++unit) {
             const int sb = two_bufs ? (unit_counter & 1) : 0;
             uint8_t* stage_buf = sStage + sb * kStageBufBytes;
-            uint32_t acc[32];
-            ptx::tmem_ld_32x32(t_row + sub * 32, acc);
-            if (sub_in_unit == 0) {
-                // the TMA store that last read this staging buffer must have finished reading
-                if (store_thread) {
-                    if (two_bufs) ptx::tma_store_wait_read<1>();
-                    else ptx::tma_store_wait_read<0>();
-                }
-                ptx::bar_sync(bar_id, kEpiThreads);
-                if (p.has_res && store_thread) {
-                    ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
-                    ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * unit_ch, x0,
-                                     y0, n0);
-                }
+            uint32_t acc[CW];
+            ptx::tmem_ld_cols(t_row + unit * kUnitCh, acc);
+            // the TMA store that last read this staging buffer must have finished reading
+            if (store_thread) {
+                if (two_bufs) ptx::tma_store_wait_read<1>();
+                else ptx::tma_store_wait_read<0>();
+            }
+            ptx::bar_sync(bar_id, kEpiThreads);
+            if (p.has_res && store_thread) {
+                ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
+                ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, y0, n0);
             }
             ptx::tmem_ld_wait();
-            if (sub == BN / 32 - 1) {
-                // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+            if (unit == kUnits - 1) {
+                // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -260,67 +289,92 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                     else ptx::mbar_arrive(&tempty_bar[g]);
                 }
             }
-            float v[32];
+            float v[CW];
+            if (p.act == kActSiluTanh) {
+                // SiLU(x) = hh * tanh(hh) + hh with hh = x / 2; sBias holds bias / 2.  Packed f32x2 FMAs (FFMA2): the
+                // accumulator registers of tcgen05.ld and the LDS.128 bias words are already adjacent pairs.
+                uint64_t hh[CW / 2];
+                const uint64_t half2 = ptx::pack_f32x2(0.5f, 0.5f);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {   // accumulator + bias (bias read as 8 x LDS.128 broadcasts)
-                const float4 b = *reinterpret_cast<const float4*>(bias + sub * 32 + 4 * j4);
-                v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
-                v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
-                v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
-                v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
-            }
-            if (p.has_add) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 a = *reinterpret_cast<const float4*>(add_row + sub * 4096 + ((j4 ^ add_xr) << 4));
-                    v[4 * j4 + 0] += a.x;
-                    v[4 * j4 + 1] += a.y;
-                    v[4 * j4 + 2] += a.z;
-                    v[4 * j4 + 3] += a.w;
+                for (int j4 = 0; j4 < CW / 4; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + unit * kUnitCh + 4 * j4);
+                    hh[2 * j4 + 0] = ptx::ffma2(ptx::pack_u32x2(acc[4 * j4 + 0], acc[4 * j4 + 1]), half2, ptx::pack_f32x2(b.x, b.y));
+                    hh[2 * j4 + 1] = ptx::ffma2(ptx::pack_u32x2(acc[4 * j4 + 2], acc[4 * j4 + 3]), half2, ptx::pack_f32x2(b.z, b.w));
                 }
-                if (sub == BN / 32 - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&add_empty[g]);
+                if (p.has_add) {
+                    const int col0 = unit * kUnitCh + h * CW;             // first channel of this thread inside the N block
+                    const uint8_t* arow = add_row + (col0 >> 5) * 4096;   // 32-channel slice
+                    const int chunk0 = (col0 & 31) >> 2;
+#pragma unroll
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const float4 a = *reinterpret_cast<const float4*>(arow + (((chunk0 + j4) ^ add_xr) << 4));
+                        hh[2 * j4 + 0] = ptx::ffma2(ptx::pack_f32x2(a.x, a.y), half2, hh[2 * j4 + 0]);
+                        hh[2 * j4 + 1] = ptx::ffma2(ptx::pack_f32x2(a.z, a.w), half2, hh[2 * j4 + 1]);
+                    }
                 }
-            }
-            if (p.act == WT_ACT_SILU) {
-                // v * sigmoid(v) with ex2.approx + rcp.approx (2 MUFU): relative error ~1e-6 everywhere.
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
-            } else if (p.act == kActSiluTanh) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float h = 0.5f * v[j];
-                    v[j] = fmaf(h, tanh_fast(h), h);
-                }
-            }
-            if (p.has_res && sub_in_unit == 0)
-                ptx::mbar_wait(&res_bar[sb], (two_bufs ? (unit_counter >> 1) : unit_counter) & 1);
-
-            if (p.out_f32) {
-                // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B
-                uint8_t* rowp = stage_buf + row * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    *reinterpret_cast<float4*>(rowp + ((c ^ (row & 7)) << 4)) = o;
+                for (int j = 0; j < CW / 2; ++j) {
+                    float lo, hi;
+                    ptx::unpack_f32x2(hh[j], lo, hi);
+                    const uint64_t t2 = ptx::pack_f32x2(tanh_fast(lo), tanh_fast(hi));
+                    ptx::unpack_f32x2(ptx::ffma2(hh[j], t2, hh[j]), v[2 * j], v[2 * j + 1]);
                 }
             } else {
-                // 32 bf16 = 64 B = 4 chunks of 16 B
+#pragma unroll
+                for (int j4 = 0; j4 < CW / 4; ++j4) {   // accumulator + bias (bias read as LDS.128 broadcasts)
+                    const float4 b = *reinterpret_cast<const float4*>(bias + unit * kUnitCh + 4 * j4);
+                    v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
+                    v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
+                    v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
+                    v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
+                }
+                if (p.has_add) {
+                    const int col0 = unit * kUnitCh + h * CW;
+                    const uint8_t* arow = add_row + (col0 >> 5) * 4096;
+                    const int chunk0 = (col0 & 31) >> 2;
+#pragma unroll
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const float4 a = *reinterpret_cast<const float4*>(arow + (((chunk0 + j4) ^ add_xr) << 4));
+                        v[4 * j4 + 0] += a.x;
+                        v[4 * j4 + 1] += a.y;
+                        v[4 * j4 + 2] += a.z;
+                        v[4 * j4 + 3] += a.w;
+                    }
+                }
+                if (p.act == WT_ACT_SILU) {
+                    // v * sigmoid(v) with ex2.approx + rcp.approx (2 MUFU): relative error ~1e-6 everywhere.
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                }
+            }
+            if (p.has_add && unit == kUnits - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&add_empty[g]);
+            }
+            if (p.has_res) ptx::mbar_wait(&res_bar[sb], (two_bufs ? (unit_counter >> 1) : unit_counter) & 1);
+
+            if (CW == 16 && p.out_f32) {
+                // 32 f32 = 128 B per row, 8 chunks of 16 B, SWIZZLE_128B; this thread's half = 4 chunks
+                uint8_t* rowp = stage_buf + row * 128;
+#pragma unroll
+                for (int c = 0; c < CW / 4; ++c) {
+                    float4 o = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    *reinterpret_cast<float4*>(rowp + (((h * 4 + c) ^ (row & 7)) << 4)) = o;
+                }
+            } else {
+                // CW bf16 = CW / 8 chunks of 16 B at chunk h * CW / 8 of the row
                 uint8_t* rowp;
-                int cbase, xr;
-                if (rows64) {
+                int xr;
+                if (CW == 16) {
                     rowp = stage_buf + row * 64;
-                    cbase = 0;
                     xr = (row >> 1) & 3;
                 } else {
                     rowp = stage_buf + row * 128;
-                    cbase = sub_in_unit * 4;
                     xr = row & 7;
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4* dstp = reinterpret_cast<uint4*>(rowp + (((cbase + c) ^ xr) << 4));
+                for (int c = 0; c < CW / 8; ++c) {
+                    uint4* dstp = reinterpret_cast<uint4*>(rowp + (((h * (CW / 8) + c) ^ xr) << 4));
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = v[8 * c + j];
@@ -341,18 +395,37 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
                     *dstp = o;
                 }
             }
-            if (sub_in_unit == subs_per_unit - 1) {
-                ptx::fence_proxy_async_smem();
-                ptx::bar_sync(bar_id, kEpiThreads);
-                if (store_thread) {
-                    ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * unit_ch, x0, y0, n0);
-                    ptx::tma_store_commit();
-                }
-                ++unit_counter;
+            ptx::fence_proxy_async_smem();
+            ptx::bar_sync(bar_id, kEpiThreads);
+            if (store_thread) {
+                ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * kUnitCh, x0, y0, n0);
+                ptx::tma_store_commit();
             }
+            ++unit_counter;
         }
     }
     if (store_thread) ptx::tma_store_wait<0>();
+}
+
+template <int BN, int CG>
+__device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
+                                              uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
+                                              uint32_t tmem_base, int warp, int lane, int rank,
+                                              const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
+                                              uint64_t* add_empty = nullptr) {
+    if (p.dot_w) {
+        conv_epilogue_dot<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane, rank);
+        return;
+    }
+    if constexpr (BN >= 64) {
+        if (!p.out_f32) {
+            conv_epilogue_cw<BN, CG, 32>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane,
+                                         rank, sAddAll, add_full, add_empty);
+            return;
+        }
+    }
+    conv_epilogue_cw<BN, CG, 16>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane, rank,
+                                 sAddAll, add_full, add_empty);
 }
 
 template <int BN, int BK, int CG>
@@ -402,12 +475,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4 * CG);   // 4 epilogue warps per CTA of the pair
+            ptx::mbar_init(&tempty_bar[i], 8 * CG);   // 8 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&add_full[i], 1);
-            ptx::mbar_init(&add_empty[i], 4);
+            ptx::mbar_init(&add_empty[i], 8);
         }
         ptx::fence_mbar_init();
     }
@@ -421,7 +494,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     }
     // whole bias vector -> smem once per CTA
-    for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
+    {
+        const float bscale = p.act == kActSiluTanh ? 0.5f : 1.0f;   // tanh form of SiLU works on (acc + bias) / 2
+        for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = bscale * __ldg(p.bias + i);
+    }
     if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();
@@ -664,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4 * CG);   // 4 epilogue warps per CTA of the pair
+            ptx::mbar_init(&tempty_bar[i], 8 * CG);   // 8 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         ptx::fence_mbar_init();
@@ -679,7 +755,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
     }
     // whole bias vector -> smem once per CTA
-    for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = __ldg(p.bias + i);
+    {
+        const float bscale = p.act == kActSiluTanh ? 0.5f : 1.0f;   // tanh form of SiLU works on (acc + bias) / 2
+        for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[i] = bscale * __ldg(p.bias + i);
+    }
     if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     ptx::tc_fence_before();

@@ -132,6 +132,13 @@ __device__ __forceinline__ void conv0_unpack(const Conv0Raw& r, float (&in)[9]) 
     in[8] = byte_to_float<3>(r.v.y);
 }
 
+// packed fp32 pair FMA (sm_100 FFMA2): d = a * (x, x) + d on two channels at once; the scalar operand is broadcast
+// by the instruction itself, so the 288 FMAs of a thread's row step are 144 issue slots
+__device__ __forceinline__ void ffma2_bcast(uint64_t& acc, float x, uint64_t w) {
+    uint64_t xx;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(w));
+}
 template <int COUT>
 __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
                                                               const float* __restrict__ w9,
@@ -154,14 +161,18 @@ __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __r
     const int y_end = min(y_begin + kConv0Rows, ho);
     const uint8_t* img = src + size_t(n) * h * w;
 
-    // weights are constants: loaded while the previous kernel (the crop / letterbox) may still be draining
+    // weights are constants: loaded while the previous kernel (the crop / letterbox) may still be draining.
+    // SiLU(v) = hh * tanh(hh) + hh with hh = v / 2: weights and bias are halved here (exact), so the FMA chain
+    // yields hh directly.  Channel pairs (2j, 2j + 1) live in one 64-bit register pair for FFMA2.
     ptx::grid_launch_dependents();
-    float wreg[9][8], breg[8];
+    const float ws = act == WT_ACT_SILU ? 0.5f : 1.0f;
+    uint64_t wreg[9][4], breg[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        breg[j] = __ldg(bias + g * 8 + j);
+    for (int j = 0; j < 4; ++j) {
+        breg[j] = ptx::pack_f32x2(ws * __ldg(bias + g * 8 + 2 * j), ws * __ldg(bias + g * 8 + 2 * j + 1));
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wreg[t][j] = __ldg(w9 + (g * 8 + j) * 9 + t);
+        for (int t = 0; t < 9; ++t)
+            wreg[t][j] = ptx::pack_f32x2(ws * __ldg(w9 + (g * 8 + 2 * j) * 9 + t), ws * __ldg(w9 + (g * 8 + 2 * j + 1) * 9 + t));
     }
     ptx::grid_dependency_wait();
     Conv0Raw raw0 = conv0_load_row(img, w, h, 2 * y_begin - 1, x0);
@@ -176,45 +187,53 @@ __global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __r
         // strip are only read inside the image, rows past the image return zeros without a load)
         raw1 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 2, x0);
         raw2 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 3, x0);
-        float acc[4][8];
+        uint64_t acc[4][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p][j] = breg[j];
+            for (int j = 0; j < 4; ++j) acc[p][j] = breg[j];
+        // same summation order per channel as the scalar form: rows 2y-1, 2y, 2y+1, taps left to right
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r0[2 * p + kw], wreg[kw][j], acc[p][j]);
+                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r0[2 * p + kw], wreg[kw][j]);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r1[2 * p + kw], wreg[3 + kw][j], acc[p][j]);
+                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r1[2 * p + kw], wreg[3 + kw][j]);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(r2[2 * p + kw], wreg[6 + kw][j], acc[p][j]);
+                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r2[2 * p + kw], wreg[6 + kw][j]);
         __nv_bfloat16* out = dst + ((size_t(n) * ho + y) * wo + x0) * dct + dcoff + g * 8;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            float o[8];
+            uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = act == WT_ACT_SILU ? silu_f(acc[p][j]) : acc[p][j];
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(o[2], o[3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(o[6], o[7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(out + size_t(p) * dct) = pk;
+            for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                if (act == WT_ACT_SILU) {
+                    ptx::unpack_f32x2(acc[p][j], lo, hi);
+                    float tl, th;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
+                    uint64_t o = acc[p][j];
+                    const uint64_t t2 = ptx::pack_f32x2(tl, th);
+                    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(o) : "l"(acc[p][j]), "l"(t2));
+                    ptx::unpack_f32x2(o, lo, hi);
+                } else {
+                    ptx::unpack_f32x2(acc[p][j], lo, hi);
+                }
+                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+                pk[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(out + size_t(p) * dct) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
 #pragma unroll
         for (int c = 0; c < 9; ++c) r0[c] = r2[c];
