@@ -344,6 +344,8 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
             if o["kind"] == L.WT_OP_CONV:
                 h, w = hp.det.program.bufs[o["dst"]][:2]
                 conv_flops += 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 + (2 * h * w * o["cout"] if o.get("dot_off", -1) >= 0 else 0)
+                if o.get("chain_w_off", -1) >= 0:      # the chained 1x1 conv (cout -> cout) runs in the same launch
+                    conv_flops += 2 * h * w * o["cout"] * o["cout"]
         conv_flops *= B
 
     if rank != 0:

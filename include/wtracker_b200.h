@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 4
+#define WT_ABI_VERSION 6
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -101,6 +101,21 @@ typedef struct wt_op {
                                  /* activation.  A 1x1 conv over concat(upsample2x(a), b) is split by    */
                                  /* linearity into conv_a(a) at half resolution (this addend, bias       */
                                  /* included) + conv_b(b): the upsampled tensor is never materialised.   */
+    int32_t lane;                /* 0 = the caller's stream; 1 = the engine's side stream.  Ops are launched in    */
+                                 /* program order; an op that reads or overwrites what an op of the OTHER lane     */
+                                 /* wrote or read waits for it through an event (the engine derives the hazards    */
+                                 /* from the buffer ids and channel ranges), and the caller's stream joins the    */
+                                 /* side stream before wt_engine_forward returns.  Independent branches (the head  */
+                                 /* of one pyramid level vs the rest of the neck) then overlap: the drain of one   */
+                                 /* persistent kernel is filled by the ramp-up of the other lane's next kernel.   */
+    int32_t chain_act;           /* CONV only: activation of the chained conv below (WT_ACT_*)                      */
+    int64_t chain_w_off;         /* CONV only, -1 = none.  Otherwise a 1x1 convolution cout -> cout is CHAINED onto  */
+    int64_t chain_b_off;         /* this one: dst receives act2(W2 * bf16(act(conv(src))) + b2).  Byte offsets of   */
+                                 /* bf16 [cout][cout] and f32 bias[cout].  The intermediate map is rounded to bf16  */
+                                 /* exactly as if it had been stored, but only exists as tiles in shared memory     */
+                                 /* (they are the A operand of a second UMMA chain).  Needs cout = 64 | 128, no      */
+                                 /* residual / addend / dot head.  (YOLOv8: a stride-2 conv followed by C2f.cv1,     */
+                                 /* which is the only consumer of the conv's output.)                               */
 } wt_op;
 
 typedef struct wt_engine wt_engine;
@@ -209,6 +224,10 @@ int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, i
  * returns the max abs difference (bf16 outputs) in *max_abs_diff; prints one line when verbose. */
 int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int k, int stride, int act,
                      int with_residual, int out_f32, int verbose, double* max_abs_diff);
+/* Chained form (wt_op.chain_w_off): conv (k, stride, SiLU) followed by a 1x1 conv cout -> cout (SiLU), once as ONE
+ * chained launch and once as two tcgen05 launches through a bf16 buffer; the results must be identical.  */
+int wt_selftest_conv_chain(int batch, int h, int w, int cin, int cout, int k, int stride, int verbose,
+                           double* max_abs_diff);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,29 @@ CASES = [
     (64, 20, 20, 512, 512, 1, 1, 1, 0, 0),   # many K blocks per tile through a short ring
 ]
 
+# chained conv + 1x1 (wt_selftest_conv_chain): batch, h, w, cin, cout, k, stride
+CHAIN_CASES = [
+    (2, 32, 32, 64, 64, 1, 1),        # generic kernel, one K block each
+    (2, 32, 32, 32, 64, 3, 2),        # layer 1 family: stride-2 pixel-pair halo kernel + chain
+    (2, 32, 32, 64, 128, 3, 2),       # layer 3 family: generic stride-2 kernel, two staging units
+    (3, 64, 48, 32, 64, 3, 2),        # ragged rows
+    (2, 32, 32, 64, 64, 3, 1),        # stride-1 halo kernel + chain
+    (40, 320, 320, 32, 64, 3, 2),     # layer 1 at depth
+    (24, 160, 160, 64, 128, 3, 2),    # layer 3 at depth
+]
+
+CHAIN_SNIPPET = """
+import ctypes, sys
+from wtracker_b200._lib import lib
+args = [int(v) for v in sys.argv[1].split(',')]
+d = ctypes.c_double(-1.0)
+rc = lib().wt_selftest_conv_chain(*args, 1, ctypes.byref(d))
+if rc != 0:
+    print('ERROR', lib().wt_last_error().decode())
+    sys.exit(2)
+sys.exit(0 if d.value == 0.0 else 3)
+"""
+
 SNIPPET = """
 import ctypes, sys
 from wtracker_b200._lib import lib
@@ -69,6 +92,8 @@ def main() -> int:
     tight = set() if "--one" in sys.argv else set(TIGHT_CASES)
     if "--one" not in sys.argv and "--quick" not in sys.argv:
         cases = cases + TIGHT_CASES
+    if "--chain-only" in sys.argv:
+        cases = []
     for case in cases:
         arg = ",".join(str(v) for v in case)
         t0 = time.time()
@@ -82,6 +107,23 @@ def main() -> int:
         if status != "OK":
             failed += 1
         print(f"[{status}] {arg} ({time.time() - t0:.1f}s) {out}", flush=True)
+    n_chain = 0
+    if "--one" not in sys.argv:
+        for case in (CHAIN_CASES[:3] if "--quick" in sys.argv else CHAIN_CASES):
+            arg = ",".join(str(v) for v in case)
+            t0 = time.time()
+            n_chain += 1
+            try:
+                res = subprocess.run([sys.executable, "-c", CHAIN_SNIPPET, arg], capture_output=True, text=True,
+                                     timeout=int(os.environ.get("WT_CASE_TIMEOUT", "40")))
+                status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
+                out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()
+            except subprocess.TimeoutExpired:
+                status, out = "TIMEOUT", ""
+            if status != "OK":
+                failed += 1
+            print(f"[{status}] chain {arg} ({time.time() - t0:.1f}s) {out}", flush=True)
+    cases = list(cases) + [None] * n_chain
     print(f"{len(cases) - failed}/{len(cases)} conv selftests passed")
     return 1 if failed else 0
 

@@ -46,6 +46,8 @@ for i, o in enumerate(ops):
     ms = float(per[i])
     h, w, c, _ = eng.program.bufs[o["dst"]]
     flop = 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 * batch if o["kind"] in (0, 1) else 0
+    if o.get("chain_w_off", -1) >= 0:
+        flop += 2 * h * w * o["cout"] * o["cout"] * batch
     rows.append((ms, i, o["name"], o["cin"], o["cout"], o["k"], o["stride"], h, flop))
 s = sum(r[0] for r in rows)
 print(f"sum of per-op times: {s:.3f} ms")

@@ -44,6 +44,9 @@ class WtOp(C.Structure):
         ("act", C.c_int32),
         ("w_off", C.c_int64), ("b_off", C.c_int64), ("dot_off", C.c_int64),
         ("add_buf", C.c_int32), ("add_coff", C.c_int32),
+        ("lane", C.c_int32),
+        ("chain_act", C.c_int32),
+        ("chain_w_off", C.c_int64), ("chain_b_off", C.c_int64),
     ]
 
 
@@ -100,6 +103,7 @@ SIGNATURES = {
     "wt_bbox_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mse_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_selftest_conv": (C.c_int, [C.c_int] * 11 + [C.POINTER(C.c_double)]),
+    "wt_selftest_conv_chain": (C.c_int, [C.c_int] * 8 + [C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -123,7 +127,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 4:
+        if handle.wt_abi_version() != 6:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

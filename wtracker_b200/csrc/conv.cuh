@@ -20,6 +20,11 @@ struct ConvDesc {
     const __nv_bfloat16* w;     // [cout][k][k][cin]
     const float* bias;          // [cout]
     const float* dot_w;         // fused 1-channel 1x1 head (wt_op.dot_off): f32 [cout + 1], or nullptr
+    // chained 1x1 conv (wt_op.chain_w_off): dst receives act2(W2 * bf16(act(conv(src))) + b2), cout -> cout channels;
+    // the intermediate map only ever exists as bf16 tiles in shared memory.  nullptr = none.
+    const __nv_bfloat16* chain_w;   // [cout][cout]
+    const float* chain_bias;        // [cout]
+    int chain_act;
     int batch;                  // images the buffers were sized for
 };
 

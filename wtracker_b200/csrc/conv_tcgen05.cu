@@ -75,6 +75,12 @@ struct ConvTcParams {
     // halo kernel: the layer's whole weight set (9 taps x one 64-channel block x all cout) fits in the B
     // stages, so it is loaded ONCE per CTA and stays resident: no weight re-streaming from L2 per tile
     int resident;
+    // chained 1x1 conv (ConvDesc.chain_w): W2 [BN][BN] stays resident in shared memory as BN / 64 K blocks, the
+    // epilogue's bf16 staging tiles are the A operand of a second UMMA chain (issued by warp 2) into accumulators
+    // 2, 3 (TMEM columns 2 * BN ...), and a second epilogue pass applies bias2 / act2 and stores
+    CUtensorMap tmB2;
+    const float* bias2;
+    int chain, act2;
     // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
     // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
     // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
@@ -407,12 +413,158 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
     if (store_thread) ptx::tma_store_wait<0>();
 }
 
+// Chained form (ConvTcParams.chain, n_blocks == 1, bf16 in / out, BN = 64 | 128).  Per tile the group
+//   1. drains accumulator g, applies bias / act and writes the bf16 tile into its BN / 64 staging buffers, which
+//      are exactly the K-major SWIZZLE_128B A operand of a 128 x BN x BN GEMM;
+//   2. signals a2_full[g]; warp 2 issues the second UMMA chain (B = W2, resident) into accumulator 2 + g;
+//   3. waits t2full[g], drains accumulator 2 + g with bias2 / act2 into the same staging buffers (the MMAs that
+//      read them have completed) and TMA-stores them.
+// cb = chain barriers: a2_full[2], t2full[2], t2empty[2].
+template <int BN, int CG>
+__device__ __forceinline__ void conv_epilogue_chain(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
+                                                    uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* cb,
+                                                    uint32_t tmem_base, int warp, int lane, int rank) {
+    constexpr int CW = 32;
+    constexpr int kUnits = BN / 64;
+    const int ew = warp - kFirstEpiWarp;
+    const int g = ew >> 3, h = (ew >> 2) & 1;
+    const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool store_thread = (et == 0);
+    uint8_t* sStage = sStageAll + g * p.epi_bufs * kStageBufBytes;
+    uint64_t* a2_full = cb + g;
+    uint64_t* t2full = cb + 2 + g;
+    uint64_t* t2empty = cb + 4 + g;
+    const int bar_id = kEpiBarrier + g;
+    const int xr = row & 7;
+    int it = g;
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    ptx::grid_dependency_wait();
+    for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const uint32_t aphase = (it >> 1) & 1;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * CW;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* bias = sBias + pass * BN + h * CW;
+            const int act = pass ? p.act2 : p.act;
+            if (pass == 0) {
+                ptx::mbar_wait(&tfull_bar[g], aphase);
+                // the stores of this group's previous tile must have finished reading the staging buffers
+                if (store_thread) ptx::tma_store_wait_read<0>();
+            } else {
+                ptx::mbar_wait(t2full, aphase);
+            }
+            ptx::tc_fence_after();
+            ptx::bar_sync(bar_id, kEpiThreads);
+#pragma unroll 1
+            for (int unit = 0; unit < kUnits; ++unit) {
+                uint32_t acc[CW];
+                ptx::tmem_ld_cols(t_row + (pass ? 2 * BN : 0) + g * BN + unit * 64, acc);
+                ptx::tmem_ld_wait();
+                if (unit == kUnits - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(pass ? t2empty : &tempty_bar[g]);
+                }
+                float v[CW];
+                if (act == kActSiluTanh) {
+                    const uint64_t half2 = ptx::pack_f32x2(0.5f, 0.5f);
+#pragma unroll
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + unit * 64 + 4 * j4);
+                        uint64_t h0 = ptx::ffma2(ptx::pack_u32x2(acc[4 * j4 + 0], acc[4 * j4 + 1]), half2, ptx::pack_f32x2(b.x, b.y));
+                        uint64_t h1 = ptx::ffma2(ptx::pack_u32x2(acc[4 * j4 + 2], acc[4 * j4 + 3]), half2, ptx::pack_f32x2(b.z, b.w));
+                        float l0, l1, l2, l3;
+                        ptx::unpack_f32x2(h0, l0, l1);
+                        ptx::unpack_f32x2(h1, l2, l3);
+                        ptx::unpack_f32x2(ptx::ffma2(h0, ptx::pack_f32x2(tanh_fast(l0), tanh_fast(l1)), h0), v[4 * j4 + 0], v[4 * j4 + 1]);
+                        ptx::unpack_f32x2(ptx::ffma2(h1, ptx::pack_f32x2(tanh_fast(l2), tanh_fast(l3)), h1), v[4 * j4 + 2], v[4 * j4 + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < CW / 4; ++j4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias + unit * 64 + 4 * j4);
+                        v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b.x;
+                        v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b.y;
+                        v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b.z;
+                        v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b.w;
+                    }
+                    if (act == WT_ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                    }
+                }
+                uint8_t* rowp = sStage + unit * kStageBufBytes + row * 128;
+#pragma unroll
+                for (int c = 0; c < CW / 8; ++c) {
+                    uint4 o;
+                    o.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+                    o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+                    o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+                    o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(rowp + (((h * 4 + c) ^ xr) << 4)) = o;
+                }
+            }
+            ptx::fence_proxy_async_smem();   // the tile is read by the async proxy: UMMA (pass 0) or the TMA store (pass 1)
+            ptx::bar_sync(bar_id, kEpiThreads);
+            if (store_thread) {
+                if (pass == 0) {
+                    ptx::mbar_arrive(a2_full);
+                } else {
+                    for (int unit = 0; unit < kUnits; ++unit)
+                        ptx::tma_store_4d(&p.tmD, sStage + unit * kStageBufBytes, p.dst_coff + unit * 64, tc.x0, tc.y0, tc.n0);
+                    ptx::tma_store_commit();
+                }
+            }
+        }
+    }
+    if (store_thread) ptx::tma_store_wait<0>();
+}
+
+// Second UMMA chain of the chained form, one elected lane of warp 2: A = the epilogue group's staging tiles,
+// B = W2 (resident, BN / 64 K blocks of [BN rows][128 B]), D = accumulator 2 + g.
+template <int BN, int CG>
+__device__ __forceinline__ void conv_chain_issuer(const ConvTcParams& p, const uint8_t* sStageAll, const uint8_t* sW2,
+                                                  uint64_t* cb, uint64_t* w2_full, uint32_t tmem_base) {
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const uint64_t b_desc0 = ptx::make_kmajor_desc<128>(ptx::smem_u32(sW2));
+    const uint32_t b_hi = uint32_t(b_desc0 >> 32), b_lo0 = uint32_t(b_desc0);
+    ptx::mbar_wait(w2_full, 0);
+    ptx::tc_fence_after();
+    int it = 0;
+    for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+        const int g = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const uint64_t a_desc0 = ptx::make_kmajor_desc<128>(ptx::smem_u32(sStageAll + g * p.epi_bufs * kStageBufBytes));
+        const uint32_t a_hi = uint32_t(a_desc0 >> 32), a_lo0 = uint32_t(a_desc0);
+        ptx::mbar_wait(cb + 4 + g, ph ^ 1);   // t2empty: the group drained accumulator 2 + g (two tiles ago)
+        ptx::mbar_wait(cb + g, ph);           // a2_full: the bf16 tile is in the staging buffers
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + 2 * BN + g * BN;
+#pragma unroll
+        for (int kb = 0; kb < BN / 64; ++kb)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_bf16_lohi(d_tmem, a_lo0 + kb * (kStageBufBytes >> 4) + 2 * kk, a_hi,
+                                    b_lo0 + kb * ((BN * 128) >> 4) + 2 * kk, b_hi, idesc, (kb | kk) != 0);
+        ptx::umma_commit(cb + 2 + g);         // t2full
+    }
+}
+
 template <int BN, int CG>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
                                               uint32_t tmem_base, int warp, int lane, int rank,
                                               const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
-                                              uint64_t* add_empty = nullptr) {
+                                              uint64_t* add_empty = nullptr, uint64_t* chain_bars = nullptr) {
+    if (p.chain) {
+        if constexpr ((BN == 64 || BN == 128) && CG == 1)
+            conv_epilogue_chain<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, chain_bars, tmem_base, warp, lane, rank);
+        return;
+    }
     if (p.dot_w) {
         conv_epilogue_dot<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane, rank);
         return;
@@ -436,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
     constexpr uint32_t kTmemCols = BN > 128 ? 512 : 2 * BN;   // double-buffered accumulator, a power of two >= 64
-    static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN");
+    static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 192 || BN == 256, "BN");
 
     // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
     // starts aligned, so no slack bytes are reserved) and checked once
@@ -448,7 +600,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 groups x epi_bufs x 16 KB epilogue staging
     // addend patches [2 groups][BN / 32][32 px][128 B], 1024-byte aligned like everything before them (128-byte swizzle)
     const uint8_t* sAdd = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;
-    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sAdd) + (p.has_add ? add_smem_bytes(BN) : 0));   // [kMaxCout]
+    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sAdd) + (p.has_add ? add_smem_bytes(BN) : 0) +
+                                            (p.chain ? BN * BN * 2 : 0));   // [kMaxCout]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
     uint64_t* full_bar = bars;                          // [stages]  TMA -> MMA
     uint64_t* empty_bar = bars + kMaxStages;            // [stages]  MMA -> TMA
@@ -457,7 +610,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* res_bar = bars + 2 * kMaxStages + 4;      // [2][2]    residual TMA -> epilogue group
     uint64_t* add_full = bars + 2 * kMaxStages + 8;     // [2]       addend patch TMA -> epilogue group
     uint64_t* add_empty = bars + 2 * kMaxStages + 10;   // [2]       epilogue group -> addend loader
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 12);
+    uint64_t* chain_bars = bars + 2 * kMaxStages + 12;  // [6]       a2_full[2], t2full[2], t2empty[2] (chained form)
+    uint64_t* w2_full = bars + 2 * kMaxStages + 18;     //           W2 resident
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 19);
+    const uint8_t* sW2 = sAdd;                          // chained form: W2 where the addend patches would be
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -482,6 +638,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             ptx::mbar_init(&add_full[i], 1);
             ptx::mbar_init(&add_empty[i], 8);
         }
+        for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
+        ptx::mbar_init(w2_full, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -489,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
             ptx::tmem_relinquish_cg2();
         } else {
-            ptx::tmem_alloc(tmem_slot, kTmemCols);
+            ptx::tmem_alloc(tmem_slot, p.chain ? 4u * BN : kTmemCols);
             ptx::tmem_relinquish();
         }
     }
@@ -500,6 +658,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
+    if (p.chain) {   // bias of the chained 1x1 conv behind the conv bias
+        const float bscale2 = p.act2 == kActSiluTanh ? 0.5f : 1.0f;
+        for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[p.cout + i] = bscale2 * __ldg(p.bias2 + i);
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
@@ -530,6 +692,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
     }
 
+    if (warp == 2 && p.chain) {
+        // ------------------------------------------------------------------ second UMMA chain (chained 1x1 conv)
+        if constexpr ((BN == 64 || BN == 128) && CG == 1) {
+            if (ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+        }
+        __syncwarp();
+    }
+
     const int taps = p.ksize * p.ksize;
     const int num_kb = taps * p.cin_blocks;
     const int pad = p.ksize >> 1;
@@ -537,6 +707,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         // The whole warp walks the loop (uniform control flow); one elected lane issues the copies.
+        if (p.chain && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
+            ptx::prefetch_tmap(&p.tmB2);
+            ptx::mbar_expect_tx(w2_full, BN * BN * 2);
+            for (int kb = 0; kb < BN / 64; ++kb)
+                ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
+        }
+        __syncwarp();
         ptx::grid_dependency_wait();
         int stage = 0;
         uint32_t phase = 0;
@@ -638,7 +815,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, sAdd,
-                              add_full, add_empty);
+                              add_full, add_empty, chain_bars);
     }
 
     ptx::tc_fence_before();
@@ -647,7 +824,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 1) {
         ptx::tc_fence_after();
         if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
-        else ptx::tmem_dealloc(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, p.chain ? 4u * BN : kTmemCols);
     }
 }
 
@@ -709,7 +886,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint8_t* sA = smem;                                        // [kAStages] halo tiles (180 px x 128 B, swizzled)
     uint8_t* sB = smem + kAStages * kHaloABytes;               // [kBStages][BN][64] bf16
     uint8_t* sStage = sB + kBStages * L::kBBytes;
-    float* sBias = reinterpret_cast<float*>(sStage + kEpiGroups * p.epi_bufs * kStageBufBytes);
+    const uint8_t* sW2 = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;   // chained form: W2 [BN / 64][BN][64] bf16
+    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sW2) + (p.chain ? BN * BN * 2 : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
     uint64_t* afull = bars;
     uint64_t* aempty = afull + kMaxAStages;
@@ -718,7 +896,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint64_t* tfull_bar = bempty + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* res_bar = tempty_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4);
+    uint64_t* chain_bars = res_bar + 4;   // [6] a2_full[2], t2full[2], t2empty[2] (chained form)
+    uint64_t* w2_full = res_bar + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 11);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -743,6 +923,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             ptx::mbar_init(&tempty_bar[i], 8 * CG);   // 8 epilogue warps per CTA of the pair
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
+        ptx::mbar_init(w2_full, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -750,7 +932,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
             ptx::tmem_relinquish_cg2();
         } else {
-            ptx::tmem_alloc(tmem_slot, kTmemCols);
+            ptx::tmem_alloc(tmem_slot, p.chain ? 4u * BN : kTmemCols);
             ptx::tmem_relinquish();
         }
     }
@@ -761,6 +943,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
     if (p.dot_w)   // dot weights + bias behind the conv bias (host checks 2 * cout + 1 <= kMaxCout)
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
+    if (p.chain) {   // bias of the chained 1x1 conv behind the conv bias
+        const float bscale2 = p.act2 == kActSiluTanh ? 0.5f : 1.0f;
+        for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[p.cout + i] = bscale2 * __ldg(p.bias2 + i);
+    }
     ptx::tc_fence_before();
     __syncthreads();
     if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
@@ -771,8 +957,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
     ptx::grid_launch_dependents();
 
+    if (warp == 2 && p.chain) {
+        // second UMMA chain of the chained 1x1 conv
+        if constexpr ((BN == 64 || BN == 128) && CG == 1) {
+            if (ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+        }
+        __syncwarp();
+    }
+
     if (warp == 0) {
         // TMA producer: warp-uniform loop, one elected lane issues
+        if (p.chain && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
+            ptx::prefetch_tmap(&p.tmB2);
+            ptx::mbar_expect_tx(w2_full, BN * BN * 2);
+            for (int kb = 0; kb < BN / 64; ++kb)
+                ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
+        }
+        __syncwarp();
         ptx::grid_dependency_wait();
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
@@ -938,7 +1139,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         __syncwarp();
     } else {
-        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank);
+        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
+                              nullptr, nullptr, chain_bars);
     }
 
     ptx::tc_fence_before();
@@ -947,7 +1149,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     if (warp == 1) {
         ptx::tc_fence_after();
         if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
-        else ptx::tmem_dealloc(tmem_base, kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, p.chain ? 4u * BN : kTmemCols);
     }
 }
 
@@ -1027,8 +1229,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         m_tiles = (long long)ceil_div(wo, tw) * ceil_div(ho, th) * ceil_div(d.batch, tn);
     }
     int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0)
-                     : pick_bn(d.cout, m_tiles, sm_count, halo_shape && !halo_s2 && d.cin % 64 == 0);
+                     : pick_bn(d.cout, m_tiles, sm_count, d.cin % 64 == 0 && !halo_s2 && !d.add.base);
     if (d.add.base && bn > 128) bn = 128;   // the addend patch buffers (N x 128 B per epilogue group) stay small
+    if (d.chain_w) {
+        WT_REQUIRE(d.cout == 64 || d.cout == 128, "a chained 1x1 conv needs 64 or 128 channels (one N tile, 4 accumulators)");
+        WT_REQUIRE(!d.res.base && !d.add.base && !d.dot_w && d.dst.dtype == WT_DT_BF16,
+                   "a chained conv has no residual / addend / dot head and writes bf16");
+        bn = d.cout;
+    }
     WT_REQUIRE(bn != 0, "cout must be a multiple of 32");
     WT_REQUIRE(d.cout <= kMaxCout, "cout exceeds the shared-memory bias vector");
     int bk = (d.cin % 64 == 0) ? 64 : 32;
@@ -1058,7 +1266,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     // but measured 15-30 % SLOWER than single-CTA MMAs on these layer shapes (B200, round 1), so off by default;
     // WT_CONV_CG=2 selects it for N >= 128.
     static const int cg_env = getenv("WT_CONV_CG") ? atoi(getenv("WT_CONV_CG")) : 1;
-    pl->cg = (cg_env == 2 && bn >= 128 && bk == 64) ? 2 : 1;
+    pl->cg = (cg_env == 2 && bn >= 128 && bk == 64 && !d.chain_w) ? 2 : 1;
     pl->s2 = 0;
     const int cg = pl->cg;
     // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
@@ -1095,6 +1303,9 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.has_add = d.add.base ? 1 : 0;
     p.add_coff = d.add.coff;
     p.dot_w = d.dot_w;
+    p.chain = d.chain_w ? 1 : 0;
+    p.bias2 = d.chain_bias;
+    p.act2 = (d.chain_act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : d.chain_act;
     p.dot_out = d.dot_w ? static_cast<float*>(d.dst.base) : nullptr;
     p.out_w = wo;
     p.out_h = ho;
@@ -1103,7 +1314,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     // shared-memory plan
     p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
-    const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0);
+    if (d.chain_w) p.epi_bufs = bn / 64;   // the staging buffers of a group hold the whole bf16 tile (A of the second GEMM)
+    const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) + (d.chain_w ? bn * bn * 2 : 0);
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
         const int b_bytes = (bn / cg) * bk * 2;
@@ -1189,6 +1401,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const uint32_t box[2] = {uint32_t(bk), uint32_t(bn / cg)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
+    }
+    p.tmB2 = p.tmB;
+    if (d.chain_w) {   // W2 [cout][cout] bf16, K-major rows; one box = 64 input channels of every output channel
+        const uint64_t dims[2] = {uint64_t(d.cout), uint64_t(d.cout)};
+        const uint64_t str[1] = {uint64_t(d.cout) * 2};
+        const uint32_t box[2] = {64, uint32_t(d.cout)};
+        rc |= encode_tmap(&p.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.chain_w), dims, str,
+                          box, 128);
     }
     p.tmP = p.tmA[0];
     if (d.add.base) {
@@ -1330,6 +1550,7 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
         case 256642: return launch_inst<256, 64, 2>(prm, smem, grid, stream);
         case 128642: return launch_inst<128, 64, 2>(prm, smem, grid, stream);
         case 256641: return launch_inst<256, 64, 1>(prm, smem, grid, stream);
+        case 192641: return launch_inst<192, 64, 1>(prm, smem, grid, stream);
         case 128641: return launch_inst<128, 64, 1>(prm, smem, grid, stream);
         case 64641:  return launch_inst<64, 64, 1>(prm, smem, grid, stream);
         case 32641:  return launch_inst<32, 64, 1>(prm, smem, grid, stream);

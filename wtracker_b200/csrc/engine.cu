@@ -32,6 +32,13 @@ struct wt_engine {
     int sm_count = 0;
     const uint8_t* weights = nullptr;
     int64_t weight_bytes = 0;
+    // lanes (wt_op.lane): side stream for lane-1 ops, fork / join events, one event per op that an op of the other
+    // lane depends on, and per op the latest earlier op of the other lane it has a buffer hazard with (-1 = none)
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    std::vector<cudaEvent_t> done_ev;
+    std::vector<int> wait_on;
+    bool lanes = false;
 };
 
 using namespace wt;
@@ -58,8 +65,50 @@ extern "C" void wt_engine_destroy(wt_engine* e) {
     if (!e) return;
     for (ConvTcPlan* p : e->conv_plan)
         if (p) conv_tc_plan_destroy(p);
+    for (cudaEvent_t ev : e->done_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+    if (e->join_ev) cudaEventDestroy(e->join_ev);
+    if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
+
+namespace {
+struct ChanRange {
+    int buf, lo, hi;
+};
+// channel ranges an op reads / writes (whole spatial extent; images are never split between ops)
+void op_ranges(const wt_op& o, std::vector<ChanRange>& rd, std::vector<ChanRange>& wr) {
+    rd.clear();
+    wr.clear();
+    switch (o.kind) {
+        case WT_OP_CONV:
+            rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
+            if (o.res >= 0) rd.push_back({o.res, o.res_coff, o.res_coff + o.cout});
+            if (o.add_buf >= 0) rd.push_back({o.add_buf, o.add_coff, o.add_coff + o.cout});
+            if (o.dot_off >= 0) wr.push_back({o.dst, 0, 1});
+            else wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cout});
+            break;
+        case WT_OP_CONV0:
+            rd.push_back({o.src, 0, 1});
+            wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cout});
+            break;
+        case WT_OP_SPPF_POOL:
+            rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
+            wr.push_back({o.dst, o.dst_coff, o.dst_coff + 3 * o.cin});
+            break;
+        default:   // WT_OP_UPSAMPLE2X
+            rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
+            wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cin});
+    }
+}
+bool overlap(const std::vector<ChanRange>& a, const std::vector<ChanRange>& b) {
+    for (const ChanRange& x : a)
+        for (const ChanRange& y : b)
+            if (x.buf == y.buf && x.lo < y.hi && y.lo < x.hi) return true;
+    return false;
+}
+}  // namespace
 
 extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops, int n_ops, int batch,
                                 const void* weights, int64_t weight_bytes, void* workspace, int64_t workspace_bytes,
@@ -130,6 +179,19 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
                     return fail("a dot-head conv writes a 1-channel f32 buffer and has no residual", i);
                 d.dot_w = reinterpret_cast<const float*>(e->weights + o.dot_off);
             }
+            d.chain_w = nullptr;
+            d.chain_bias = nullptr;
+            d.chain_act = 0;
+            if (o.chain_w_off >= 0) {
+                if (o.chain_w_off % 16 != 0 || o.chain_b_off < 0 || o.chain_b_off % 4 != 0 ||
+                    o.chain_w_off + int64_t(o.cout) * o.cout * 2 > weight_bytes ||
+                    o.chain_b_off + int64_t(o.cout) * 4 > weight_bytes)
+                    return fail("chained conv weights out of range", i);
+                if (conv_impl != 0) return fail("chained convs exist on the tcgen05 path only", i);
+                d.chain_w = reinterpret_cast<const __nv_bfloat16*>(e->weights + o.chain_w_off);
+                d.chain_bias = reinterpret_cast<const float*>(e->weights + o.chain_b_off);
+                d.chain_act = o.chain_act;
+            }
             d.batch = batch;
             if (o.src_coff + o.cin > e->bufs[o.src].c || (!d.dot_w && o.dst_coff + o.cout > e->bufs[o.dst].c))
                 return fail("channel slice exceeds buffer", i);
@@ -147,6 +209,36 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             return fail("unknown op kind", i);
         }
     }
+    // lanes: cross-lane hazards (read-after-write, write-after-write, write-after-read) -> event waits
+    static const int lanes_env = getenv("WT_LANES") ? atoi(getenv("WT_LANES")) : 1;
+    e->wait_on.assign(n_ops, -1);
+    e->done_ev.assign(n_ops, nullptr);
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops[i].lane != 0 && ops[i].lane != 1) return fail("lane must be 0 or 1", i);
+        if (!lanes_env) e->ops[i].lane = 0;
+        if (e->ops[i].lane == 1) e->lanes = true;
+    }
+    if (e->lanes) {
+        std::vector<ChanRange> ri, wi, rj, wj;
+        for (int i = 0; i < n_ops; ++i) {
+            op_ranges(e->ops[i], ri, wi);
+            for (int j = i - 1; j >= 0; --j) {
+                if (e->ops[j].lane == e->ops[i].lane) continue;
+                op_ranges(e->ops[j], rj, wj);
+                if (overlap(wj, ri) || overlap(wj, wi) || overlap(rj, wi)) {
+                    e->wait_on[i] = j;   // the latest one: the other lane's stream orders everything before it
+                    break;
+                }
+            }
+        }
+        bool ok = cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&e->join_ev, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < n_ops && ok; ++i)
+            if (e->wait_on[i] >= 0 && !e->done_ev[e->wait_on[i]])
+                ok = cudaEventCreateWithFlags(&e->done_ev[e->wait_on[i]], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) return fail("could not create the side stream / events", 0);
+    }
     *out = e;
     return 0;
 }
@@ -160,9 +252,21 @@ extern "C" int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op,
     WT_REQUIRE(e, "null engine");
     WT_REQUIRE(n >= 0 && n <= e->batch, "n exceeds the engine batch");
     WT_REQUIRE(first_op >= 0 && last_op <= int(e->ops.size()) && first_op <= last_op, "op range");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaStream_t main_stream = static_cast<cudaStream_t>(stream_);
+    bool used_side = false;
+    int waited[2] = {-1, -1};   // per lane: the latest op of the other lane this call already waited for
     for (int i = first_op; i < last_op; ++i) {
         const wt_op& o = e->ops[i];
+        cudaStream_t stream = o.lane ? e->side : main_stream;
+        if (o.lane && !used_side) {   // fork: the side stream starts behind everything already queued by the caller
+            WT_CHECK_CUDA(cudaEventRecord(e->fork_ev, main_stream));
+            WT_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->fork_ev, 0));
+            used_side = true;
+        }
+        if (e->wait_on[i] > waited[o.lane]) {   // (an event never recorded, op outside this call's range, is a no-op)
+            WT_CHECK_CUDA(cudaStreamWaitEvent(stream, e->done_ev[e->wait_on[i]], 0));
+            waited[o.lane] = e->wait_on[i];
+        }
         int rc = 0;
         switch (o.kind) {
             case WT_OP_CONV:
@@ -186,6 +290,11 @@ extern "C" int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op,
                 rc = 1;
         }
         if (rc) return rc;
+        if (e->done_ev[i]) WT_CHECK_CUDA(cudaEventRecord(e->done_ev[i], stream));
+    }
+    if (used_side) {   // join: the caller's stream continues after the side stream's last op
+        WT_CHECK_CUDA(cudaEventRecord(e->join_ev, e->side));
+        WT_CHECK_CUDA(cudaStreamWaitEvent(main_stream, e->join_ev, 0));
     }
     return 0;
 }
@@ -255,6 +364,7 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     d.add = TensorView{nullptr, 0, 0, 0, 0, 0};
     d.cin = cin; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
     d.w = d_w; d.bias = d_bias; d.dot_w = nullptr; d.batch = batch;
+    d.chain_w = nullptr; d.chain_bias = nullptr; d.chain_act = 0;
     ConvTcPlan* plan = nullptr;
     int rc = conv_tc_plan_create(d, &plan);
     if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);
@@ -277,5 +387,72 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     if (verbose)
         printf("selftest_conv b%d %dx%d cin%d cout%d k%d s%d act%d res%d f32%d : max|diff| %.5g (ref max %.4g)\n", batch, h, w,
                cin, cout, k, stride, act, with_residual, out_f32, stats[0], stats[1]);
+    return 0;
+}
+
+extern "C" int wt_selftest_conv_chain(int batch, int h, int w, int cin, int cout, int k, int stride, int verbose,
+                                      double* max_abs_diff) {
+    int sm = 0, cc = 0;
+    if (wt_device_info(&sm, &cc, nullptr)) return 1;
+    const int ho = h / stride, wo = w / stride;
+    // the source fills its buffer (the stride-2 pixel-pair kernel requires it); the destination is a channel slice
+    const int dst_ct = cout + 64, dst_off = 32;
+    const size_t n_src = size_t(batch) * h * w * cin, n_mid = size_t(batch) * ho * wo * cout;
+    const size_t n_dst = size_t(batch) * ho * wo * dst_ct, n_w = size_t(cout) * k * k * cin, n_w2 = size_t(cout) * cout;
+    __nv_bfloat16 *d_src = nullptr, *d_w = nullptr, *d_w2 = nullptr, *d_mid = nullptr, *d_out = nullptr, *d_ref = nullptr;
+    float *d_bias = nullptr, *d_bias2 = nullptr, *d_stats = nullptr;
+    WT_CHECK_CUDA(cudaMalloc(&d_src, n_src * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_w, n_w * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_w2, n_w2 * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_mid, n_mid * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_out, n_dst * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_ref, n_dst * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_bias, cout * 4));
+    WT_CHECK_CUDA(cudaMalloc(&d_bias2, cout * 4));
+    WT_CHECK_CUDA(cudaMalloc(&d_stats, 8));
+    WT_CHECK_CUDA(cudaMemset(d_out, 0, n_dst * 2));
+    WT_CHECK_CUDA(cudaMemset(d_ref, 0, n_dst * 2));
+    WT_CHECK_CUDA(cudaMemset(d_stats, 0, 8));
+    fill_bf16<<<unsigned((n_src + 255) / 256), 256>>>(d_src, n_src, 1u, 1.0f);
+    fill_bf16<<<unsigned((n_w + 255) / 256), 256>>>(d_w, n_w, 2u, 1.0f / sqrtf(float(k * k * cin)));
+    fill_bf16<<<unsigned((n_w2 + 255) / 256), 256>>>(d_w2, n_w2, 5u, 2.0f / sqrtf(float(cout)));
+    fill_f32<<<unsigned((cout + 255) / 256), 256>>>(d_bias, cout, 4u, 0.5f);
+    fill_f32<<<unsigned((cout + 255) / 256), 256>>>(d_bias2, cout, 6u, 0.5f);
+    const TensorView none{nullptr, 0, 0, 0, 0, 0};
+    ConvDesc a;   // the conv, written to the intermediate buffer
+    a.src = TensorView{d_src, h, w, cin, 0, WT_DT_BF16};
+    a.dst = TensorView{d_mid, ho, wo, cout, 0, WT_DT_BF16};
+    a.res = none; a.add = none;
+    a.cin = cin; a.cout = cout; a.k = k; a.stride = stride; a.act = WT_ACT_SILU;
+    a.w = d_w; a.bias = d_bias; a.dot_w = nullptr; a.batch = batch;
+    a.chain_w = nullptr; a.chain_bias = nullptr; a.chain_act = 0;
+    ConvDesc b = a;   // the 1x1 conv on the intermediate buffer
+    b.src = a.dst;
+    b.dst = TensorView{d_ref, ho, wo, dst_ct, dst_off, WT_DT_BF16};
+    b.cin = cout; b.k = 1; b.stride = 1; b.w = d_w2; b.bias = d_bias2;
+    ConvDesc c = a;   // both in one launch
+    c.dst = TensorView{d_out, ho, wo, dst_ct, dst_off, WT_DT_BF16};
+    c.chain_w = d_w2; c.chain_bias = d_bias2; c.chain_act = WT_ACT_SILU;
+    int rc = 0;
+    for (const ConvDesc* d : {&a, &b, &c}) {
+        ConvTcPlan* plan = nullptr;
+        if (!rc) rc = conv_tc_plan_create(*d, &plan);
+        if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);
+        if (plan) conv_tc_plan_destroy(plan);
+    }
+    float stats[2] = {0, 0};
+    if (!rc) {
+        max_diff_kernel<<<unsigned((n_dst + 255) / 256), 256>>>(d_out, d_ref, n_dst, 0, d_stats, d_stats + 1);
+        cudaError_t e1 = cudaDeviceSynchronize();
+        if (e1 != cudaSuccess) { set_error(std::string("selftest kernel failed: ") + cudaGetErrorString(e1)); rc = 1; }
+        else cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_src); cudaFree(d_w); cudaFree(d_w2); cudaFree(d_mid); cudaFree(d_out); cudaFree(d_ref);
+    cudaFree(d_bias); cudaFree(d_bias2); cudaFree(d_stats);
+    if (rc) return rc;
+    if (max_abs_diff) *max_abs_diff = stats[0];
+    if (verbose)
+        printf("selftest_conv_chain b%d %dx%d cin%d cout%d k%d s%d : max|diff| %.5g (ref max %.4g)\n", batch, h, w, cin, cout,
+               k, stride, stats[0], stats[1]);
     return 0;
 }

@@ -5,6 +5,8 @@
 #include "conv.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace wt {
 
 namespace {
@@ -139,8 +141,8 @@ __device__ __forceinline__ void ffma2_bcast(uint64_t& acc, float x, uint64_t w) 
     asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(w));
 }
-template <int COUT>
-__global__ void __launch_bounds__(kConv0Threads) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
+template <int COUT, int MINB>
+__global__ void __launch_bounds__(kConv0Threads, MINB) conv0_kernel(const uint8_t* __restrict__ src, int h, int w,
                                                               const float* __restrict__ w9,
                                                               const float* __restrict__ bias, int act,
                                                               __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
@@ -357,7 +359,10 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
     const int threads = kConv0Threads;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dst.base);
-    auto* kernel = cout == 32 ? conv0_kernel<32> : (cout == 16 ? conv0_kernel<16> : conv0_kernel<64>);
+    // WT_CONV0_OCC=4 caps registers at 128 (4 CTAs / SM, a few spilled words) for A/B runs; default 3 CTAs / SM
+    static const int occ_env = getenv("WT_CONV0_OCC") ? atoi(getenv("WT_CONV0_OCC")) : 3;
+    auto* kernel = cout == 32 ? (occ_env == 4 ? conv0_kernel<32, 4> : conv0_kernel<32, 3>)
+                              : (cout == 16 ? conv0_kernel<16, 3> : conv0_kernel<64, 3>);
     WT_CHECK_CUDA(launch_pdl(kernel, dim3(blocks), dim3(threads), 0, stream, src, h, w, w9, bias, act, out, dst.ctot,
                              dst.coff, total));
     WT_LAUNCHED();

@@ -6,6 +6,8 @@ PyTorch is plumbing here (memory + streams); all arithmetic happens in libwtrack
 
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import numpy as np
@@ -44,7 +46,8 @@ class DetectorEngine:
         self.lb: Letterbox = letterbox_for(view_hw, imgsz)
         self.batch = int(batch)
         self.conf, self.iou, self.max_det = float(conf), float(iou), int(max_det)
-        self.program: Program = build_program(state_dict, self.arch, self.lb.dst_h, self.lb.dst_w)
+        self.program: Program = build_program(state_dict, self.arch, self.lb.dst_h, self.lb.dst_w,
+                                              chain=conv_impl == 0 and os.environ.get("WT_CHAIN", "1") != "0")
 
         with torch.cuda.device(self.device):
             self.weights = blob_tensor(self.program).to(self.device)

@@ -56,7 +56,9 @@ def _align(blob: bytearray, a: int) -> int:
     return len(blob)
 
 
-def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net_w: int) -> Program:
+def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net_w: int, chain: bool = True) -> Program:
+    """``chain``: chain C2f.cv1 onto the stride-2 conv before it where the engine supports it (wt_op.chain_w_off;
+    tcgen05 path only, so the scalar validation engine is built with chain=False)."""
     assert net_h % 32 == 0 and net_w % 32 == 0, "network input must be a multiple of 32"
     assert arch.nc == 1, "the fused class-logit path is written for single-class models (reference: single_cls)"
     p = Program(arch, net_h, net_w)
@@ -139,14 +141,32 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
                           cout=s.cout, k=s.k, stride=s.stride, act=L.WT_ACT_SILU if s.bn_act else L.WT_ACT_NONE,
                           w_off=w_off, b_off=b_off, dot_off=dot_off))
 
-    def c2f(idx: int, src, dst: tuple[int, int], down: int):
+    chained: list[str] = []
+
+    def c2f(idx: int, src, dst: tuple[int, int], down: int, after: tuple[str, tuple[int, int]] | None = None):
         """``src`` is (buffer, channel offset) or, for the two neck blocks fed by concat(upsample(a), b),
-        a dict(low=(buf, coff), c_low=.., high=(buf, coff), c_high=..)."""
+        a dict(low=(buf, coff), c_low=.., high=(buf, coff), c_high=..).  ``after`` = (name, source) of the conv
+        whose output is ``src`` and has no other consumer: cv1 is then chained onto it and ``src`` is never written."""
         spec = arch.c2f[idx]
         cc = spec.c
         cat = new_buf(f"c2f{idx}.cat", down, (2 + spec.n) * cc)
         tmp = new_buf(f"c2f{idx}.tmp", down, cc)
-        if isinstance(src, dict):
+        s1 = specs[f"model.{idx}.cv1"]
+        if (chain and after is not None and s1.cin == s1.cout and s1.cout in (64, 128) and s1.k == 1
+                and specs[after[0]].cout == s1.cin):
+            conv(after[0], after[1], (cat, 0))
+            w2, b2 = folded_conv(sd, s1)
+            w2_off = _align(p.blob, 16)
+            p.blob.extend(w2.reshape(s1.cout, s1.cin).contiguous().to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+            b2_off = _align(p.blob, 16)
+            p.blob.extend(b2.float().numpy().tobytes())
+            p.ops[-1].update(name=f"{after[0]}>model.{idx}.cv1", chain_w_off=w2_off, chain_b_off=b2_off,
+                             chain_act=L.WT_ACT_SILU if s1.bn_act else L.WT_ACT_NONE)
+            chained.append(after[0])
+        elif after is not None:
+            conv(after[0], after[1], src)
+            conv(f"model.{idx}.cv1", src, (cat, 0))
+        elif isinstance(src, dict):
             conv_over_upsampled_cat(f"model.{idx}.cv1", src["low"], src["c_low"], src["high"], src["c_high"], (cat, 0),
                                     down)
         else:
@@ -183,14 +203,11 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     p.blob.extend(bias0.float().numpy().tobytes())
     p.ops.append(dict(kind=L.WT_OP_CONV0, name="model.0", src=b_in, src_coff=0, dst=b0, dst_coff=0, res=-1, res_coff=0,
                       cin=1, cout=c[0], k=3, stride=2, act=L.WT_ACT_SILU, w_off=w_off, b_off=b_off))
-    conv("model.1", (b0, 0), (b1, 0))
-    c2f(2, (b1, 0), (b2, 0), 4)
-    conv("model.3", (b2, 0), (b3, 0))
-    c2f(4, (b3, 0), (b4, 0), 8)                   # x4
-    conv("model.5", (b4, 0), (b5, 0))
-    c2f(6, (b5, 0), (b6, 0), 16)                  # x6
-    conv("model.7", (b6, 0), (b7, 0))
-    c2f(8, (b7, 0), (b8, 0), 32)
+    # a stride-2 conv of the backbone feeds only the C2f after it: cv1 is chained onto it where the shapes allow
+    c2f(2, (b1, 0), (b2, 0), 4, after=("model.1", (b0, 0)))
+    c2f(4, (b3, 0), (b4, 0), 8, after=("model.3", (b2, 0)))                    # x4
+    c2f(6, (b5, 0), (b6, 0), 16, after=("model.5", (b4, 0)))                   # x6
+    c2f(8, (b7, 0), (b8, 0), 32, after=("model.7", (b6, 0)))
     conv("model.9.cv1", (b8, 0), (sppf, 0))
     p.ops.append(dict(kind=L.WT_OP_SPPF_POOL, name="model.9.m", src=sppf, src_coff=0, dst=sppf, dst_coff=c[4] // 2,
                       res=-1, res_coff=0, cin=c[4] // 2, cout=c[4] // 2, k=5, stride=1, act=0, w_off=0, b_off=0))
@@ -229,13 +246,48 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
         p.head.append(dict(box_feat=t2, box_w_off=bw_off, box_b_off=bb_off, box_c=arch.box_c, cls_logit=logit,
                            h=net_h // down, w=net_w // down, stride=STRIDES[lvl]))
     _align(p.blob, 16)
+    _assign_lanes(p)
 
     p.taps = {
         "x4": (b4, 0, c[2]), "x6": (b6, 0, c[3]), "x9": (cat20, c[3], c[4]),
         "x12": (cat17, c[2], c[3]), "x15": (b15, 0, c[2]), "x18": (b18, 0, c[3]), "x21": (b21, 0, c[4]),
         "m0": (b0, 0, c[0]), "m1": (b1, 0, c[1]), "m2": (b2, 0, c[1]), "m3": (b3, 0, c[2]),
     }
+    for name, tap in (("model.1", "m1"), ("model.3", "m3")):
+        if name in chained:
+            del p.taps[tap]      # never written: it only exists as tiles inside the chained kernel
     return p
+
+
+def _assign_lanes(p: Program) -> None:
+    """Two launch lanes (wt_op.lane) for the part of the graph that has independent branches: once x15 exists, the
+    heads of pyramid levels 0 and 1 (lane 1, the engine's side stream) run beside the rest of the neck and the
+    level-2 head (lane 0).  Every kernel is persistent with one CTA per SM, so two lanes do not share SMs; what
+    overlaps is the drain of one kernel (last tiles, partial last wave) with the ramp-up of the other lane's next
+    kernel, which on one stream is a dependency bubble after every launch.  The order stays topological (the engine
+    derives cross-lane waits from earlier ops only) and alternates lanes so both queues stay fed."""
+    names = [o["name"] for o in p.ops]
+    if "model.16" not in names:
+        return
+    start = names.index("model.16")
+    tail = p.ops[start:]
+    head = {lvl: [o for o in tail if o["name"].startswith(("model.22.cv2.%d." % lvl, "model.22.cv3.%d." % lvl))]
+            for lvl in range(3)}
+    neck = [o for o in tail if not o["name"].startswith("model.22.")]
+    x18 = max(i for i, o in enumerate(neck) if o["name"].startswith("model.18."))   # model.18.cv2 writes x18
+    for o in head[0] + head[1]:
+        o["lane"] = 1
+    order: list[dict] = []
+    side = list(head[0])
+    for i, o in enumerate(neck):
+        order.append(o)
+        if i == x18:
+            side += head[1]          # level 1 reads x18: only after its producer in program order
+        if side:
+            order.append(side.pop(0))
+    order += side + head[2]
+    assert len(order) == len(tail) and {id(o) for o in order} == {id(o) for o in tail}
+    p.ops[start:] = order
 
 
 def ops_as_ctypes(p: Program):
@@ -243,7 +295,8 @@ def ops_as_ctypes(p: Program):
     ops = (L.WtOp * len(p.ops))()
     for i, o in enumerate(p.ops):
         ops[i] = L.WtOp(o["kind"], o["src"], o["src_coff"], o["dst"], o["dst_coff"], o["res"], o["res_coff"],
-                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1), o.get("add_buf", -1), o.get("add_coff", 0))
+                        o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1), o.get("add_buf", -1), o.get("add_coff", 0),
+                        o.get("lane", 0), o.get("chain_act", 0), o.get("chain_w_off", -1), o.get("chain_b_off", -1))
     return bufs, ops
 
 
