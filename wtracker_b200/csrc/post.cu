@@ -208,15 +208,30 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     __syncthreads();
 
     // ---- (a) confidence + filter (logits are ready: either given or computed by cls_logit_kernel)
-    for (int a = tid; a < A; a += kPostThreads) {
-        const int l = level_of(p, a);
-        const wt_head_level& L = p.lv[l];
-        const float logit = L.cls_logit ? __ldg(L.cls_logit + size_t(img) * L.h * L.w + (a - p.level_start[l]))
-                                        : p.sc_logit[size_t(img) * A + a];
-        const float conf = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logit)));
-        if (conf > p.pp.conf_thres) {
-            const int pos = atomicAdd(&s_count, 1);
-            keys[pos] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - unsigned(a));
+    // eight anchors per thread and trip: all eight logit loads are in flight before the first one is used (one
+    // dependent load per trip made this loop a chain of ~17 DRAM latencies per image)
+    constexpr int kPostUnroll = 8;
+    for (int a0 = tid; a0 < A; a0 += kPostUnroll * kPostThreads) {
+        float lg[kPostUnroll];
+#pragma unroll
+        for (int u = 0; u < kPostUnroll; ++u) {
+            const int a = a0 + u * kPostThreads;
+            lg[u] = 0.f;
+            if (a < A) {
+                const int l = level_of(p, a);
+                const wt_head_level& L = p.lv[l];
+                lg[u] = L.cls_logit ? __ldg(L.cls_logit + size_t(img) * L.h * L.w + (a - p.level_start[l]))
+                                    : p.sc_logit[size_t(img) * A + a];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPostUnroll; ++u) {
+            const int a = a0 + u * kPostThreads;
+            const float conf = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-lg[u])));
+            if (a < A && conf > p.pp.conf_thres) {
+                const int pos = atomicAdd(&s_count, 1);
+                keys[pos] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - unsigned(a));
+            }
         }
     }
     __syncthreads();

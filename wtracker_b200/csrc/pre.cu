@@ -9,6 +9,8 @@
 #include "../../include/wtracker_b200.h"
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace wt {
 namespace {
 
@@ -47,10 +49,41 @@ __global__ void __launch_bounds__(256) pre_kernel(const PreParams p) {
         for (int i = 0; i < 16; ++i) px[i] = 114;
     } else if (!RESIZE) {
         const uint8_t* srow = frame + size_t(clampi(cy + ry, 0, p.fh - 1)) * p.fw;
+        const int rx0 = X0 - p.lb.pad_left;
+        const uint8_t* src = srow + cx + rx0;
+        // Interior fast path (all 16 pixels inside the view and the frame, one more group of slack to the right so
+        // the second vector load stays inside the row): two aligned 128-bit loads, byte-aligned with funnel shifts.
+        // The crop origin is arbitrary, so the misalignment m is only uniform per image row.
+        if (rx0 >= 0 && rx0 + 16 <= p.lb.new_w && cx + rx0 >= 0 && cx + rx0 + 32 <= p.fw) {
+            const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src)) & 15u;
+            const uint4* base = reinterpret_cast<const uint4*>(src - m);
+            const uint4 lo = __ldg(base), hi = __ldg(base + 1);
+            const uint32_t sh = (m & 3u) * 8u;
+            uint32_t w0, w1, w2, w3, w4;
+            switch (m >> 2) {
+                case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+                case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+                case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+                default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+            }
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh);
+            v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh);
+            v.w = __funnelshift_r(w3, w4, sh);
+            if (p.out_u8 && (p.lb.dst_w & 15) == 0 && !p.out_f32) {   // product path: straight to the 128-bit store
+                *reinterpret_cast<uint4*>(p.out_u8 + (size_t(img) * p.lb.dst_h + Y) * p.lb.dst_w + X0) = v;
+                return;
+            }
+            const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int rx = X0 + i - p.lb.pad_left;
-            px[i] = (rx >= 0 && rx < p.lb.new_w) ? __ldg(srow + clampi(cx + rx, 0, p.fw - 1)) : uint8_t(114);
+            for (int i = 0; i < 16; ++i) px[i] = uint8_t(vw[i >> 2] >> ((i & 3) * 8));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rx = rx0 + i;
+                px[i] = (rx >= 0 && rx < p.lb.new_w) ? __ldg(srow + clampi(cx + rx, 0, p.fw - 1)) : uint8_t(114);
+            }
         }
     } else {
         // vertical taps: rows yofs, yofs+1 of the VIEW, clipped to the view, then to the frame
@@ -103,6 +136,77 @@ __global__ void __launch_bounds__(256) pre_kernel(const PreParams p) {
     }
 }
 
+// Resize path of the product (u8-only) output.  The kernel above gives every thread 16 adjacent output pixels, so a
+// warp's byte gathers touch ~4 cache lines per load and the resize ran at 3-5 % of HBM bandwidth (L1 wavefront
+// bound).  Here one CTA produces kResizeRows output rows of one image: the source rows it needs are staged ONCE in
+// shared memory with coalesced, clamp-addressed loads (== BORDER_REPLICATE), a thread owns output COLUMNS (its
+// horizontal taps and weights stay in registers) and walks the rows, so shared-memory reads and global stores of a
+// warp are contiguous.  Same integer arithmetic as above: bit-exact against cv2.resize's fixed-point model.
+constexpr int kResizeThreads = 256;
+constexpr int kResizeRows = 16;
+
+__global__ void __launch_bounds__(kResizeThreads) pre_resize_kernel(const PreParams p, int pitch) {
+    extern __shared__ uint8_t s_rows[];   // [rows of this tile][pitch]
+    __shared__ int s_r0[kResizeRows], s_r1[kResizeRows], s_b0[kResizeRows], s_b1[kResizeRows];
+    const wt_letterbox& lb = p.lb;
+    const int img = blockIdx.y, Y0 = blockIdx.x * kResizeRows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows_here = min(kResizeRows, lb.dst_h - Y0);
+    const uint8_t* frame = p.frames + size_t(p.frame_idx[img]) * p.fh * p.fw;
+    const int cx = p.crop_x[img], cy = p.crop_y[img];
+
+    // view rows this tile reads: [vbase, vtop]
+    const int ry_lo = max(Y0 - lb.pad_top, 0), ry_hi = min(Y0 + rows_here - lb.pad_top, lb.new_h) - 1;
+    int vbase = 0, nrows = 0;
+    if (ry_lo <= ry_hi) {
+        vbase = clampi(lb.yofs[ry_lo], 0, lb.src_h - 1);
+        nrows = clampi(lb.yofs[ry_hi] + 1, 0, lb.src_h - 1) - vbase + 1;
+    }
+    if (tid < rows_here) {
+        const int ry = Y0 + tid - lb.pad_top;
+        int r0 = -1, r1 = -1, b0 = 0, b1 = 0;
+        if (ry >= 0 && ry < lb.new_h) {
+            const int sy = lb.yofs[ry];
+            r0 = (clampi(sy, 0, lb.src_h - 1) - vbase) * pitch;
+            r1 = (clampi(sy + 1, 0, lb.src_h - 1) - vbase) * pitch;
+            b0 = lb.ycoef[2 * ry];
+            b1 = lb.ycoef[2 * ry + 1];
+        }
+        s_r0[tid] = r0; s_r1[tid] = r1; s_b0[tid] = b0; s_b1[tid] = b1;
+    }
+    for (int r = warp; r < nrows; r += kResizeThreads / 32) {
+        const uint8_t* srow = frame + size_t(clampi(cy + vbase + r, 0, p.fh - 1)) * p.fw;
+        for (int c = lane; c < lb.src_w; c += 32) s_rows[r * pitch + c] = __ldg(srow + clampi(cx + c, 0, p.fw - 1));
+    }
+    __syncthreads();
+
+    uint8_t* out = p.out_u8 + (size_t(img) * lb.dst_h + Y0) * lb.dst_w;
+    for (int x = tid; x < lb.dst_w; x += kResizeThreads) {
+        const int rx = x - lb.pad_left;
+        const bool col_in = rx >= 0 && rx < lb.new_w;
+        int sx = 0, sx1 = 0, a0 = 0, a1 = 0;
+        if (col_in) {
+            sx = lb.xofs[rx];
+            sx1 = sx + 1 < lb.src_w ? sx + 1 : sx;
+            a0 = lb.xcoef[2 * rx];
+            a1 = lb.xcoef[2 * rx + 1];
+        }
+#pragma unroll 4
+        for (int j = 0; j < rows_here; ++j) {
+            const int r0 = s_r0[j];
+            int v = 114;
+            if (col_in && r0 >= 0) {
+                const uint8_t* q0 = s_rows + r0;
+                const uint8_t* q1 = s_rows + s_r1[j];
+                const int h0 = int(q0[sx]) * a0 + int(q0[sx1]) * a1;
+                const int h1 = int(q1[sx]) * a0 + int(q1[sx1]) * a1;
+                v = clampi((((s_b0[j] * (h0 >> 4)) >> 16) + ((s_b1[j] * (h1 >> 4)) >> 16) + 2) >> 2, 0, 255);
+            }
+            out[size_t(j) * lb.dst_w + x] = uint8_t(v);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace wt
 
@@ -130,6 +234,23 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
     p.out_f32 = out_f32;
     const int groups = ((lb->dst_w + 15) / 16) * lb->dst_h;
     dim3 grid((groups + 255) / 256, n);
+    if (resize && out_u8 && !out_f32) {
+        // rows of the view one 16-row output tile can touch (+1 for the second tap, +2 for rounding at both ends)
+        const int max_rows = std::min(lb->src_h, ((kResizeRows - 1) * lb->src_h + lb->new_h - 1) / lb->new_h + 3);
+        const int pitch = (lb->src_w + 15) & ~15;
+        const int smem = max_rows * pitch;
+        if (smem <= 200 * 1024) {
+            static int configured = 0;
+            if (smem > configured) {
+                WT_CHECK_CUDA(cudaFuncSetAttribute(pre_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                configured = 200 * 1024;
+            }
+            dim3 rgrid((lb->dst_h + kResizeRows - 1) / kResizeRows, n);
+            pre_resize_kernel<<<rgrid, kResizeThreads, smem, static_cast<cudaStream_t>(stream)>>>(p, pitch);
+            WT_LAUNCHED();
+            return 0;
+        }
+    }
     if (resize) pre_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     else pre_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     WT_LAUNCHED();
