@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 6
+#define WT_ABI_VERSION 7
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -216,6 +216,20 @@ int wt_mlp_gather(const double* table, int64_t table_rows, const int32_t* frame,
 /* ------------------------------------------------------------------------------------------ */
 int wt_bbox_error(const double* worm_xywh, const double* mic_xywh, double* err, int64_t n, void* stream);
 int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, int64_t n, void* stream);
+
+/* Rows of the tracking log `bboxes.csv` for n consecutive frames starting at first_frame (replaces the per-frame
+ * part of LoggingController._log_cycle, wtracker/sim/sim_controllers/logging_controller.py:145-185, and
+ * BoxUtils.discretize, wtracker/utils/bbox_utils.py:119-167):
+ *   worm_rel  : [n][4] camera-relative worm boxes (x, y, w, h), f64 or f32 (worm_is_f32), NaN row = no prediction
+ *   cam_xywh, mic_xywh : i32 [n][4] camera / microscope boxes; plt_xy : i32 [n][2] platform positions
+ *   table     : f64 [n][17] = frame, cycle, phase (0 imaging | 1 moving), plt_x, plt_y, cam_x, cam_y, cam_w, cam_h,
+ *               mic_x, mic_y, mic_w, mic_h, wrm_x, wrm_y, wrm_w, wrm_h   (the csv column order; wrm absolute,
+ *               rows without a prediction are 0, 0, 0, 0 exactly as the reference logs them)
+ *   crop_xywh : i32 [n][4] integer crop of the worm view clipped to the frame (0 if empty), crop_legal: u8 [n]
+ * cycle = frame / cycle_frame_num, phase = (frame % cycle_frame_num) < imaging_frame_num.                          */
+int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t* cam_xywh, const int32_t* mic_xywh,
+                const int32_t* plt_xy, int64_t n, int64_t first_frame, int cycle_frame_num, int imaging_frame_num,
+                int frame_h, int frame_w, double* table, int32_t* crop_xywh, uint8_t* crop_legal, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* test-only helpers (allocate + synchronise; never called by the product path)               */

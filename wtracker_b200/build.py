@@ -26,6 +26,7 @@ SOURCES = [
     "post.cu",
     "resmlp.cu",
     "metrics.cu",
+    "log.cu",
     "engine.cu",
 ]
 
