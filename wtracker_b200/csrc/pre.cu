@@ -136,6 +136,55 @@ __global__ void __launch_bounds__(256) pre_kernel(const PreParams p) {
     }
 }
 
+// Pure crop (view == network input, no letterbox padding, u8 output only): the product path of the 640x640
+// configuration.  One thread moves a 16-pixel x 4-row block: the three per-image index loads are amortised over 128
+// bytes, and all eight 128-bit loads are issued before the first store.
+constexpr int kCropRows = 4;
+
+__device__ __forceinline__ uint4 load16_unaligned(const uint8_t* src) {
+    const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src)) & 15u;
+    const uint4* base = reinterpret_cast<const uint4*>(src - m);
+    const uint4 lo = __ldg(base), hi = __ldg(base + 1);
+    const uint32_t sh = (m & 3u) * 8u;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (m >> 2) {
+        case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+        case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+        case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+        default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                      __funnelshift_r(w3, w4, sh));
+}
+
+__global__ void __launch_bounds__(256) pre_crop_kernel(const PreParams p) {
+    const int groups_per_row = p.lb.dst_w >> 4;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    if (gid >= groups_per_row * (p.lb.dst_h / kCropRows)) return;
+    const int Yq = gid / groups_per_row;
+    const int X0 = (gid - Yq * groups_per_row) << 4;
+    const uint8_t* frame = p.frames + size_t(p.frame_idx[img]) * p.fh * p.fw;
+    const int cx = p.crop_x[img], cy = p.crop_y[img];
+    const bool x_in = cx + X0 >= 0 && cx + X0 + 32 <= p.fw;   // one group of slack for the second vector load
+    uint4 v[kCropRows];
+#pragma unroll
+    for (int r = 0; r < kCropRows; ++r) {
+        const uint8_t* srow = frame + size_t(clampi(cy + Yq * kCropRows + r, 0, p.fh - 1)) * p.fw;
+        if (x_in) {
+            v[r] = load16_unaligned(srow + cx + X0);
+        } else {   // the view hangs over the left / right frame border: replicate per byte
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i >> 2] |= uint32_t(__ldg(srow + clampi(cx + X0 + i, 0, p.fw - 1))) << ((i & 3) * 8);
+            v[r] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    uint8_t* o = p.out_u8 + (size_t(img) * p.lb.dst_h + Yq * kCropRows) * p.lb.dst_w + X0;
+#pragma unroll
+    for (int r = 0; r < kCropRows; ++r) *reinterpret_cast<uint4*>(o + size_t(r) * p.lb.dst_w) = v[r];
+}
+
 // Resize path of the product (u8-only) output.  The kernel above gives every thread 16 adjacent output pixels, so a
 // warp's byte gathers touch ~4 cache lines per load and the resize ran at 3-5 % of HBM bandwidth (L1 wavefront
 // bound).  Here one CTA produces kResizeRows output rows of one image: the source rows it needs are staged ONCE in
@@ -234,6 +283,13 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
     p.out_f32 = out_f32;
     const int groups = ((lb->dst_w + 15) / 16) * lb->dst_h;
     dim3 grid((groups + 255) / 256, n);
+    if (!resize && out_u8 && !out_f32 && lb->pad_left == 0 && lb->pad_top == 0 && lb->new_w == lb->dst_w &&
+        lb->new_h == lb->dst_h && lb->dst_w % 16 == 0 && lb->dst_h % kCropRows == 0) {
+        const int cgroups = (lb->dst_w / 16) * (lb->dst_h / kCropRows);
+        pre_crop_kernel<<<dim3((cgroups + 255) / 256, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        WT_LAUNCHED();
+        return 0;
+    }
     if (resize && out_u8 && !out_f32) {
         // rows of the view one 16-row output tile can touch (+1 for the second tap, +2 for rounding at both ends)
         const int max_rows = std::min(lb->src_h, ((kResizeRows - 1) * lb->src_h + lb->new_h - 1) / lb->new_h + 3);
