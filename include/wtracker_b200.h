@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 7
+#define WT_ABI_VERSION 8
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -230,6 +230,20 @@ int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, i
 int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t* cam_xywh, const int32_t* mic_xywh,
                 const int32_t* plt_xy, int64_t n, int64_t first_frame, int cycle_frame_num, int imaging_frame_num,
                 int frame_h, int frame_w, double* table, int32_t* crop_xywh, uint8_t* crop_legal, void* stream);
+
+/* Segmentation-based tracking error (replaces ErrorCalculator.calculate_precise / calculate_segmentation,
+ * wtracker/eval/error_calculator.py:19-161): for row i the fraction of the segmented worm — pixels of the
+ * discretized worm box whose |frame - background| exceeds diff_thresh — that lies outside the microscope box.
+ *   frames : u8 [n_frames][frame_h][frame_w] grey frames in HBM; frame_idx : i32 [n] frame of each row (the worm
+ *            view the reference reads through `worm_reader` is that frame cropped at the discretized worm box)
+ *   view_off : NULL, or i64 [n]: `frames` is then a packed buffer of the rows' own crops (row-major, w x h of the
+ *            discretized worm box) and row i's crop starts at byte view_off[i]; frame_idx is not read
+ *   background : u8 [frame_h][frame_w];  worm_xywh, mic_xywh : f64 [n][4]
+ *   err : f64 [n]: 0 when nothing is segmented, NaN when the worm box is non-finite or empty after clipping.
+ * (The reference writes the results of the legal rows to err[0..n_legal): that quirk is applied by the host mirror.) */
+int wt_precise_error(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* frame_idx,
+                     const int64_t* view_off, const uint8_t* background, const double* worm_xywh, const double* mic_xywh, double diff_thresh,
+                     double* err, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* test-only helpers (allocate + synchronise; never called by the product path)               */

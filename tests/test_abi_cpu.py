@@ -11,7 +11,7 @@ def test_header_symbols_are_exported(native_lib):
     header = (ROOT / "include" / "wtracker_b200.h").read_text()
     declared = set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", header))
     declared -= {"wt_engine"}
-    assert len(declared) == 20
+    assert len(declared) == 21
     from wtracker_b200 import _lib
 
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
@@ -20,7 +20,7 @@ def test_header_symbols_are_exported(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.wt_abi_version() == 7
+    assert native_lib.wt_abi_version() == 8
     assert isinstance(native_lib.wt_last_error(), bytes)
     assert native_lib.wt_launch_count() >= 0
 

@@ -102,6 +102,8 @@ SIGNATURES = {
                                 C.c_int64, C.c_void_p]),
     "wt_bbox_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mse_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "wt_precise_error": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_log_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wt_selftest_conv": (C.c_int, [C.c_int] * 11 + [C.POINTER(C.c_double)]),
@@ -129,7 +131,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 7:
+        if handle.wt_abi_version() != 8:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

@@ -27,6 +27,7 @@ SOURCES = [
     "resmlp.cu",
     "metrics.cu",
     "log.cu",
+    "precise.cu",
     "engine.cu",
 ]
 
