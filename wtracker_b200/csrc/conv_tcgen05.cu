@@ -1314,6 +1314,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     // shared-memory plan
     p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
+    static const int epi_env = getenv("WT_EPI_BUFS") ? atoi(getenv("WT_EPI_BUFS")) : 0;   // A/B knob: 1 | 2 everywhere
+    if (epi_env == 1 || epi_env == 2) p.epi_bufs = epi_env;
     if (d.chain_w) p.epi_bufs = bn / 64;   // the staging buffers of a group hold the whole bf16 tile (A of the second GEMM)
     const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) + (d.chain_w ? bn * bn * 2 : 0);
     if (pl->halo) {

@@ -95,7 +95,7 @@ __global__ void conv_dot_simt_kernel(const __nv_bfloat16* __restrict__ src, int 
 // group are loaded once and stay in registers, the 3-row input window slides (one 8-byte + one 1-byte
 // load per new input row), and the four lanes of a pixel quad together store 64 contiguous bytes per
 // pixel.  Issue-bound on the FMA/MUFU pipes (~14 instructions per output), not on HBM.
-constexpr int kConv0Rows = 8;
+constexpr int kConv0Rows = 20;
 constexpr int kConv0Threads = 128;
 
 struct Conv0Raw {   // one input row segment as loaded: columns 2*x0 .. 2*x0+7 and column 2*x0-1
@@ -180,15 +180,21 @@ __global__ void __launch_bounds__(kConv0Threads, MINB) conv0_kernel(const uint8_
     Conv0Raw raw0 = conv0_load_row(img, w, h, 2 * y_begin - 1, x0);
     Conv0Raw raw1 = conv0_load_row(img, w, h, 2 * y_begin, x0);
     Conv0Raw raw2 = conv0_load_row(img, w, h, 2 * y_begin + 1, x0);
+    Conv0Raw raw3 = conv0_load_row(img, w, y_begin + 1 < y_end ? h : 0, 2 * y_begin + 2, x0);
+    Conv0Raw raw4 = conv0_load_row(img, w, y_begin + 1 < y_end ? h : 0, 2 * y_begin + 3, x0);
     float r0[9], r1[9], r2[9];          // input rows 2y-1, 2y, 2y+1
     conv0_unpack(raw0, r0);
     for (int y = y_begin; y < y_end; ++y) {
         conv0_unpack(raw1, r1);
         conv0_unpack(raw2, r2);
-        // prefetch the next output row's two new input rows a whole iteration ahead (rows past the
-        // strip are only read inside the image, rows past the image return zeros without a load)
-        raw1 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 2, x0);
-        raw2 = conv0_load_row(img, w, y + 1 < y_end ? h : 0, 2 * y + 3, x0);
+        // the two new input rows of an output row are loaded TWO iterations ahead: one iteration (~1.2 us of this
+        // warp's time at 12 warps / SM) is about one DRAM latency under load, and ncu showed 20 % of the warp time
+        // waiting for the one-ahead prefetch.  (Rows past the strip are only read inside the image, rows past the
+        // image return zeros without a load.)
+        raw1 = raw3;
+        raw2 = raw4;
+        raw3 = conv0_load_row(img, w, y + 2 < y_end ? h : 0, 2 * y + 4, x0);
+        raw4 = conv0_load_row(img, w, y + 2 < y_end ? h : 0, 2 * y + 5, x0);
         uint64_t acc[4][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
