@@ -95,7 +95,7 @@ __global__ void conv_dot_simt_kernel(const __nv_bfloat16* __restrict__ src, int 
 // group are loaded once and stay in registers, the 3-row input window slides (one 8-byte + one 1-byte
 // load per new input row), and the four lanes of a pixel quad together store 64 contiguous bytes per
 // pixel.  Issue-bound on the FMA/MUFU pipes (~14 instructions per output), not on HBM.
-constexpr int kConv0Rows = 20;
+constexpr int kConv0Rows = 16;
 constexpr int kConv0Threads = 128;
 
 struct Conv0Raw {   // one input row segment as loaded: columns 2*x0 .. 2*x0+7 and column 2*x0-1
