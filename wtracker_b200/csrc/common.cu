@@ -79,11 +79,20 @@ uint64_t wt_launch_count(void) { return wt::g_launch_count.load(); }
 int wt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     WT_CHECK_CUDA(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    WT_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (sm_count) *sm_count = prop.multiProcessorCount;
-    if (cc_major) *cc_major = prop.major;
-    if (cc_minor) *cc_minor = prop.minor;
+    // attribute queries (microseconds), not cudaGetDeviceProperties (milliseconds): this is called on launch paths
+    int v = 0;
+    if (sm_count) {
+        WT_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        *sm_count = v;
+    }
+    if (cc_major) {
+        WT_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev));
+        *cc_major = v;
+    }
+    if (cc_minor) {
+        WT_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev));
+        *cc_minor = v;
+    }
     return 0;
 }
 

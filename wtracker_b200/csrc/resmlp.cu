@@ -6,6 +6,7 @@
 // conflict-free [feature][thread] layout.  fp32 FMA throughout.
 #include "../../include/wtracker_b200.h"
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace wt {
 namespace {
@@ -87,6 +88,130 @@ __global__ void __launch_bounds__(kMlpThreads) resmlp_kernel(const MlpParams p) 
     for (int i = t; i < valid * od; i += kMlpThreads) {
         const int s = i / od, f = i - s * od;
         p.y[base * od + i] = t0[f * kLd + s];
+    }
+}
+
+// Large batches, two samples per thread: the pair shares every weight load and every issue slot — the weight of
+// neuron o for input i is ONE broadcast scalar of a packed f32x2 FMA (FFMA2) whose two lanes are the two samples.
+// Weights are staged transposed, [in][out padded to 8], so eight neurons' weights are two LDS.128 broadcasts; per
+// input that is 1 LDS.64 (the activation pair) + 2 LDS.128 + 8 FFMA2 for 16 MACs, where the one-sample kernel above
+// needs 5 loads + 4 FMAs for 4.  Each neuron still accumulates bias first, then its inputs in order, so all three
+// kernels give bit-identical results.  The last layer of a block adds straight into the residual stream.
+constexpr int kPairThreads = 128;
+constexpr int kPairLd = kPairThreads + 1;    // leading dimension of the [feature][thread] float2 tiles
+
+__device__ __forceinline__ int pad8(int v) { return (v + 7) & ~7; }
+
+// out[o] (+)= act(bias[o] + sum_i in[i] * w[i][o]) for the thread's two samples; `into_x`: out is the residual stream
+// (`in_off` / `out_off` are offsets into the dynamic shared-memory window, not pointers: with pointers picked at run
+// time the compiler falls back to generic loads, LD.E instead of LDS)
+__device__ __forceinline__ void dense_pair(const float* __restrict__ wt, const float* __restrict__ b, int in_off,
+                                           int out_off, int nin, int nout, bool relu, bool into_x, int t) {
+    extern __shared__ __align__(16) float mlp_smem[];
+    const uint64_t* in = reinterpret_cast<const uint64_t*>(mlp_smem) + in_off;
+    uint64_t* out = reinterpret_cast<uint64_t*>(mlp_smem) + out_off;
+    const int np = pad8(nout);
+    for (int o = 0; o < np; o += 8) {
+        uint64_t a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = ptx::pack_f32x2(b[o + k], b[o + k]);
+        const float* w0 = wt + o;
+#pragma unroll 4
+        for (int i = 0; i < nin; ++i) {
+            const uint64_t v = in[i * kPairLd + t];
+            const float4 wa = *reinterpret_cast<const float4*>(w0 + i * np);
+            const float4 wb = *reinterpret_cast<const float4*>(w0 + i * np + 4);
+            a[0] = ptx::ffma2(v, ptx::pack_f32x2(wa.x, wa.x), a[0]);
+            a[1] = ptx::ffma2(v, ptx::pack_f32x2(wa.y, wa.y), a[1]);
+            a[2] = ptx::ffma2(v, ptx::pack_f32x2(wa.z, wa.z), a[2]);
+            a[3] = ptx::ffma2(v, ptx::pack_f32x2(wa.w, wa.w), a[3]);
+            a[4] = ptx::ffma2(v, ptx::pack_f32x2(wb.x, wb.x), a[4]);
+            a[5] = ptx::ffma2(v, ptx::pack_f32x2(wb.y, wb.y), a[5]);
+            a[6] = ptx::ffma2(v, ptx::pack_f32x2(wb.z, wb.z), a[6]);
+            a[7] = ptx::ffma2(v, ptx::pack_f32x2(wb.w, wb.w), a[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (o + k < nout) {
+                float lo, hi;
+                ptx::unpack_f32x2(a[k], lo, hi);
+                if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                if (into_x) {
+                    float xl, xh;
+                    ptx::unpack_f32x2(out[(o + k) * kPairLd + t], xl, xh);
+                    lo = xl + lo;
+                    hi = xh + hi;
+                }
+                out[(o + k) * kPairLd + t] = ptx::pack_f32x2(lo, hi);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPairThreads) resmlp_pair_kernel(const MlpParams p, int tw0, int tw1,
+                                                                   int n_weights_padded) {
+    extern __shared__ __align__(16) float mlp_smem[];
+    float* sw = mlp_smem;                                            // per layer: [in][pad8(out)] then bias[pad8(out)]
+    const int xs_off = n_weights_padded / 2;                         // residual stream [hidden][kPairLd] pairs
+    const int t0_off = xs_off + p.d.hidden * kPairLd;                // scratch A [tw0][kPairLd]: input, even block layers, output
+    const int t1_off = t0_off + tw0 * kPairLd;                       // scratch B [tw1][kPairLd]: odd block layers
+    uint64_t* t0 = reinterpret_cast<uint64_t*>(mlp_smem) + t0_off;
+    (void)tw1;
+    const int t = threadIdx.x;
+    const int H = p.d.hidden, ind = p.d.in_dim, od = p.d.out_dim;
+    const int n_layers = 2 + p.d.n_blocks * p.d.block_len;
+    {   // stage: transpose to [in][out], pad the outputs to a multiple of 8 with zero weights / zero bias
+        int src = 0, dst = 0, nin = ind;
+        for (int l = 0; l < n_layers; ++l) {
+            const int nout = l == 0 ? H : (l == n_layers - 1 ? od : p.d.block_dims[(l - 1) % p.d.block_len]);
+            const int np = pad8(nout);
+#pragma unroll 4
+            for (int idx = t; idx < nin * np; idx += kPairThreads) {
+                const int i = idx / np, o = idx - i * np;
+                sw[dst + idx] = o < nout ? __ldg(p.d.weights + src + o * nin + i) : 0.f;
+            }
+            for (int o = t; o < np; o += kPairThreads) sw[dst + nin * np + o] = o < nout ? __ldg(p.d.weights + src + nout * nin + o) : 0.f;
+            src += nout * nin + nout;
+            dst += nin * np + np;
+            nin = nout;
+        }
+    }
+    // persistent over chunks of 256 samples: the weights are staged once per CTA, not once per 256 samples
+    float* t0f = reinterpret_cast<float*>(t0);
+    const long long n_chunks = (p.n + 2 * kPairThreads - 1) / (2 * kPairThreads);
+    for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const long long base = chunk * (2 * kPairThreads);
+    const int valid = int(min((long long)(2 * kPairThreads), p.n - base));
+    __syncthreads();                                                     // the previous chunk's outputs have left t0
+#pragma unroll 4
+    for (int i = t; i < 2 * kPairThreads * ind; i += kPairThreads) {     // coalesced read, [feature][sample] in smem
+        const int s = i / ind, f = i - s * ind;
+        t0f[(f * kPairLd + (s >> 1)) * 2 + (s & 1)] = s < valid ? __ldg(p.x + base * ind + i) : 0.f;
+    }
+    __syncthreads();
+
+    const float* w = sw;
+    dense_pair(w, w + ind * pad8(H), t0_off, xs_off, ind, H, true, false, t);
+    w += ind * pad8(H) + pad8(H);
+    for (int blk = 0; blk < p.d.n_blocks; ++blk) {
+        int in = xs_off;
+        int nin = H;
+        for (int l = 0; l < p.d.block_len; ++l) {
+            const int nout = p.d.block_dims[l];
+            const bool last = l == p.d.block_len - 1;
+            const int out = last ? xs_off : ((l & 1) ? t1_off : t0_off);   // (block_len >= 2: the last layer never reads xs)
+            dense_pair(w, w + nin * pad8(nout), in, out, nin, nout, true, last, t);
+            w += nin * pad8(nout) + pad8(nout);
+            in = out;
+            nin = nout;
+        }
+    }
+    dense_pair(w, w + H * pad8(od), xs_off, t0_off, H, od, false, false, t);
+    __syncthreads();
+    for (int i = t; i < valid * od; i += kPairThreads) {
+        const int s = i / od, f = i - s * od;
+        p.y[base * od + i] = t0f[(f * kPairLd + (s >> 1)) * 2 + (s & 1)];
+    }
     }
 }
 
@@ -237,6 +362,39 @@ extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float*
         resmlp_warp_kernel<<<(unsigned)wblocks, kMlpWarpThreads, wsmem, static_cast<cudaStream_t>(stream)>>>(p);
         WT_LAUNCHED();
         return 0;
+    }
+    if (d->block_len >= 2) {   // two samples per thread (FFMA2)
+        // padded weight floats, and the scratch width: the input vector and every block layer but the last
+        long long wp = (long long)d->in_dim * ((d->hidden + 7) & ~7) + ((d->hidden + 7) & ~7);
+        int tw0 = d->in_dim > d->out_dim ? d->in_dim : d->out_dim, tw1 = 1, nin2 = d->hidden;
+        long long blockp = 0;
+        for (int l = 0; l < d->block_len; ++l) {
+            const int np = (d->block_dims[l] + 7) & ~7;
+            blockp += (long long)nin2 * np + np;
+            nin2 = d->block_dims[l];
+            if (l + 1 < d->block_len) {
+                int& tw = (l & 1) ? tw1 : tw0;
+                if (nin2 > tw) tw = nin2;
+            }
+        }
+        wp += blockp * d->n_blocks + (long long)d->hidden * ((d->out_dim + 7) & ~7) + ((d->out_dim + 7) & ~7);
+        wp = (wp + 3) & ~3LL;
+        const size_t psmem = size_t(wp) * 4 + size_t(d->hidden + tw0 + tw1) * kPairLd * 8;
+        if (psmem <= 220 * 1024) {
+            static size_t pconfigured = 0;
+            if (psmem > 48 * 1024 && psmem > pconfigured) {
+                WT_CHECK_CUDA(cudaFuncSetAttribute(resmlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
+                pconfigured = psmem;
+            }
+            long long pblocks = (n + 2 * kPairThreads - 1) / (2 * kPairThreads);
+            int sm_count = 148;
+            wt_device_info(&sm_count, nullptr, nullptr);
+            const long long resident = (long long)sm_count * (psmem > 110 * 1024 ? 1 : 2);
+            if (pblocks > resident) pblocks = resident;          // persistent: a CTA walks chunks blockIdx.x, + grid, ...
+            resmlp_pair_kernel<<<(unsigned)pblocks, kPairThreads, psmem, static_cast<cudaStream_t>(stream)>>>(p, tw0, tw1, int(wp));
+            WT_LAUNCHED();
+            return 0;
+        }
     }
     const size_t smem = (size_t((d->n_weights + 31) & ~31) + size_t(3) * maxw * kLd) * sizeof(float);
     WT_REQUIRE(smem <= 220 * 1024, "ResMLP too large for the shared-memory kernel");
