@@ -345,7 +345,9 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
                 h, w = hp.det.program.bufs[o["dst"]][:2]
                 conv_flops += 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 + (2 * h * w * o["cout"] if o.get("dot_off", -1) >= 0 else 0)
                 if o.get("chain_w_off", -1) >= 0:      # the chained 1x1 conv (cout -> cout) runs in the same launch
-                    conv_flops += 2 * h * w * o["cout"] * o["cout"]
+                    k2 = o["cat_c"] + o["cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]      # concat chain: K = cat slice + output
+                    n2 = o["chain_cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]
+                    conv_flops += 2 * h * w * n2 * k2
         conv_flops *= B
 
     if rank != 0:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 8
+#define WT_ABI_VERSION 9
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -116,6 +116,13 @@ typedef struct wt_op {
                                  /* (they are the A operand of a second UMMA chain).  Needs cout = 64 | 128, no      */
                                  /* residual / addend / dot head.  (YOLOv8: a stride-2 conv followed by C2f.cv1,     */
                                  /* which is the only consumer of the conv's output.)                               */
+    int32_t cat_buf, cat_coff;   /* CONV with a chain only, cat_buf = -1: none.  Otherwise a CONCAT chain: the chained  */
+    int32_t cat_c, chain_cout;   /* 1x1 conv runs over concat(channels [cat_coff, cat_coff + cat_c) of buffer cat_buf,  */
+                                 /* this conv's output) and has chain_cout outputs; chain weights are bf16              */
+                                 /* [chain_cout][cat_c + cout].  This conv's residual must be the upper half of that    */
+                                 /* slice.  Implemented for the exit of a C2f block with one bottleneck and 32 hidden   */
+                                 /* channels (3x3 32 -> 32 + y1, then cv2 over [y0 | y1 | b], 96 -> 64): the bottleneck */
+                                 /* output never leaves shared memory and [y0 | y1] is read once.                       */
 } wt_op;
 
 typedef struct wt_engine wt_engine;
@@ -256,6 +263,9 @@ int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int k, int stri
  * chained launch and once as two tcgen05 launches through a bf16 buffer; the results must be identical.  */
 int wt_selftest_conv_chain(int batch, int h, int w, int cin, int cout, int k, int stride, int verbose,
                            double* max_abs_diff);
+/* Concat chain (wt_op.cat_buf): the exit of a C2f block (3x3 32 -> 32 + residual, then 1x1 96 -> 64 over the concat
+ * buffer) as one launch vs two tcgen05 launches; the results must be identical. */
+int wt_selftest_conv_cat(int batch, int h, int w, int verbose, double* max_abs_diff);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ def test_header_symbols_are_exported(native_lib):
     header = (ROOT / "include" / "wtracker_b200.h").read_text()
     declared = set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", header))
     declared -= {"wt_engine"}
-    assert len(declared) == 21
+    assert len(declared) == 22
     from wtracker_b200 import _lib
 
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
@@ -20,7 +20,7 @@ def test_header_symbols_are_exported(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.wt_abi_version() == 8
+    assert native_lib.wt_abi_version() == 9
     assert isinstance(native_lib.wt_last_error(), bytes)
     assert native_lib.wt_launch_count() >= 0
 
@@ -29,7 +29,7 @@ def test_struct_sizes_match_header(native_lib):
     from wtracker_b200 import _lib as L
 
     # sizes printed by a C program compiled against include/wtracker_b200.h (x86-64 SysV)
-    expect = {"WtLetterbox": 64, "WtBuf": 16, "WtOp": 104, "WtPostParams": 40, "WtHeadLevel": 96, "WtResmlpDesc": 72}
+    expect = {"WtLetterbox": 64, "WtBuf": 16, "WtOp": 120, "WtPostParams": 40, "WtHeadLevel": 96, "WtResmlpDesc": 72}
     for name, size in expect.items():
         assert ctypes.sizeof(getattr(L, name)) == size, name
 

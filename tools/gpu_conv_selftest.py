@@ -56,6 +56,21 @@ CHAIN_CASES = [
     (24, 160, 160, 64, 128, 3, 2),    # layer 3 at depth
 ]
 
+# concat chain (wt_selftest_conv_cat): batch, h, w
+CAT_CASES = [(2, 16, 16), (2, 32, 32), (3, 48, 40), (40, 160, 160)]
+
+CAT_SNIPPET = """
+import ctypes, sys
+from wtracker_b200._lib import lib
+args = [int(v) for v in sys.argv[1].split(',')]
+d = ctypes.c_double(-1.0)
+rc = lib().wt_selftest_conv_cat(*args, 1, ctypes.byref(d))
+if rc != 0:
+    print('ERROR', lib().wt_last_error().decode())
+    sys.exit(2)
+sys.exit(0 if d.value == 0.0 else 3)
+"""
+
 CHAIN_SNIPPET = """
 import ctypes, sys
 from wtracker_b200._lib import lib
@@ -92,7 +107,7 @@ def main() -> int:
     tight = set() if "--one" in sys.argv else set(TIGHT_CASES)
     if "--one" not in sys.argv and "--quick" not in sys.argv:
         cases = cases + TIGHT_CASES
-    if "--chain-only" in sys.argv:
+    if "--chain-only" in sys.argv or "--cat-only" in sys.argv:
         cases = []
     for case in cases:
         arg = ",".join(str(v) for v in case)
@@ -109,12 +124,16 @@ def main() -> int:
         print(f"[{status}] {arg} ({time.time() - t0:.1f}s) {out}", flush=True)
     n_chain = 0
     if "--one" not in sys.argv:
-        for case in (CHAIN_CASES[:3] if "--quick" in sys.argv else CHAIN_CASES):
+        chain_cases = [(CHAIN_SNIPPET, c) for c in (CHAIN_CASES[:3] if "--quick" in sys.argv else CHAIN_CASES)]
+        chain_cases += [(CAT_SNIPPET, c) for c in (CAT_CASES[:2] if "--quick" in sys.argv else CAT_CASES)]
+        if "--cat-only" in sys.argv:
+            chain_cases = [(CAT_SNIPPET, c) for c in CAT_CASES]
+        for CHAIN_SNIPPET_, case in chain_cases:
             arg = ",".join(str(v) for v in case)
             t0 = time.time()
             n_chain += 1
             try:
-                res = subprocess.run([sys.executable, "-c", CHAIN_SNIPPET, arg], capture_output=True, text=True,
+                res = subprocess.run([sys.executable, "-c", CHAIN_SNIPPET_, arg], capture_output=True, text=True,
                                      timeout=int(os.environ.get("WT_CASE_TIMEOUT", "40")))
                 status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
                 out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()

@@ -47,7 +47,9 @@ for i, o in enumerate(ops):
     h, w, c, _ = eng.program.bufs[o["dst"]]
     flop = 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 * batch if o["kind"] in (0, 1) else 0
     if o.get("chain_w_off", -1) >= 0:
-        flop += 2 * h * w * o["cout"] * o["cout"] * batch
+        k2 = o["cat_c"] + o["cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]
+        n2 = o["chain_cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]
+        flop += 2 * h * w * n2 * k2 * batch
     rows.append((ms, i, o["name"], o["cin"], o["cout"], o["k"], o["stride"], h, flop))
 s = sum(r[0] for r in rows)
 print(f"sum of per-op times: {s:.3f} ms")

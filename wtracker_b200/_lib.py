@@ -47,6 +47,7 @@ class WtOp(C.Structure):
         ("lane", C.c_int32),
         ("chain_act", C.c_int32),
         ("chain_w_off", C.c_int64), ("chain_b_off", C.c_int64),
+        ("cat_buf", C.c_int32), ("cat_coff", C.c_int32), ("cat_c", C.c_int32), ("chain_cout", C.c_int32),
     ]
 
 
@@ -108,6 +109,7 @@ SIGNATURES = {
                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wt_selftest_conv": (C.c_int, [C.c_int] * 11 + [C.POINTER(C.c_double)]),
     "wt_selftest_conv_chain": (C.c_int, [C.c_int] * 8 + [C.POINTER(C.c_double)]),
+    "wt_selftest_conv_cat": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -131,7 +133,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 8:
+        if handle.wt_abi_version() != 9:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib

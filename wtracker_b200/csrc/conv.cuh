@@ -22,9 +22,13 @@ struct ConvDesc {
     const float* dot_w;         // fused 1-channel 1x1 head (wt_op.dot_off): f32 [cout + 1], or nullptr
     // chained 1x1 conv (wt_op.chain_w_off): dst receives act2(W2 * bf16(act(conv(src))) + b2), cout -> cout channels;
     // the intermediate map only ever exists as bf16 tiles in shared memory.  nullptr = none.
-    const __nv_bfloat16* chain_w;   // [cout][cout]
-    const float* chain_bias;        // [cout]
+    const __nv_bfloat16* chain_w;   // [cout][cout]   (concat chain: [chain_cout][cat_c + cout])
+    const float* chain_bias;        // [cout]         (concat chain: [chain_cout])
     int chain_act;
+    // concat chain (wt_op.cat_buf): the chained 1x1 conv runs over concat(cat slice, this conv's output); cat.base ==
+    // nullptr -> plain chain.  The conv's residual must be the upper half of the cat slice (C2f: y1 of [y0 | y1]).
+    TensorView cat;
+    int cat_c, chain_cout;
     int batch;                  // images the buffers were sized for
 };
 

@@ -80,7 +80,13 @@ struct ConvTcParams {
     // 2, 3 (TMEM columns 2 * BN ...), and a second epilogue pass applies bias2 / act2 and stores
     CUtensorMap tmB2;
     const float* bias2;
-    int chain, act2;
+    int chain, act2;   // chain: 0 none | 1 chained 1x1 (cout -> cout) | 2 concat chain (below)
+    // concat chain (ConvDesc.cat, C2f exit): the second GEMM is a 1x1 conv over concat(cat slice [64 ch], this conv's
+    // output [32 ch]) -> 64 channels.  The cat tile of the pixel patch is TMA-loaded by warp 2 (tmY; it also supplies
+    // the residual, which is its upper 32 channels), W2 = [64][96] is resident as a 64-channel K block (tmB2,
+    // SWIZZLE_128B) + a 32-channel K block (tmB2b, SWIZZLE_64B like the staging tile it multiplies).
+    CUtensorMap tmY, tmB2b;
+    int cat_coff;
     // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
     // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
     // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
@@ -554,6 +560,183 @@ __device__ __forceinline__ void conv_chain_issuer(const ConvTcParams& p, const u
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Concat chain (ConvTcParams.chain == 2): the exit of a C2f block with one bottleneck and 32 hidden channels,
+//   b   = y1 + SiLU(conv3x3(b1))                  (this launch's main GEMM, BN = 32, residual y1)
+//   out = SiLU(W2 * concat(y0, y1, b) + bias2)    (C2f.cv2, 96 -> 64)
+// as one launch: b never leaves shared memory and y = [y0 | y1] is read once (it is both the residual and two
+// thirds of the second GEMM's A operand).  Shared memory behind the staging buffers: Y[2] (one 128 px x 64 ch tile
+// per epilogue group), W2a [64][64], W2b [64][32].  Staging buffer 0 of a group holds the bf16 b tile (64-byte rows,
+// SWIZZLE_64B = K-major A operand of a K = 32 GEMM), buffer 1 the output tile.  cb: a2_full[2], t2full[2],
+// t2empty[2]; yb: y_full[2].
+constexpr int kCatC = 64, kCatOut = 64;
+constexpr int kCatSmemBytes = 2 * kStageBufBytes + kCatOut * kCatC * 2 + kCatOut * 32 * 2;   // Y[2] + W2a + W2b
+
+__device__ __forceinline__ void conv_epilogue_cat(const ConvTcParams& p, uint8_t* sStageAll, const uint8_t* sY,
+                                                  const float* sBias, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                                  uint64_t* cb, uint64_t* yb, uint32_t tmem_base, int warp, int lane) {
+    constexpr int BN = 32;
+    const int ew = warp - kFirstEpiWarp;
+    const int g = ew >> 3, h = (ew >> 2) & 1;
+    const int et = threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool store_thread = (et == 0);
+    uint8_t* sB8 = sStageAll + g * 2 * kStageBufBytes;          // b tile, 64-byte rows
+    uint8_t* sOut = sB8 + kStageBufBytes;                       // output tile, 128-byte rows
+    const uint8_t* yrow = sY + g * kStageBufBytes + row * 128;
+    const int bar_id = kEpiBarrier + g;
+    int it = g;
+    const int first = blockIdx.x, step = gridDim.x;
+    ptx::grid_dependency_wait();
+    for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+        const TileCoord tc = decode_tile<1>(p, tile, 0);
+        const uint32_t aphase = (it >> 1) & 1;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // ---- pass 0: b = y1 + act(acc + bias), bf16, into the K = 32 staging tile
+        ptx::mbar_wait(&tfull_bar[g], aphase);
+        ptx::mbar_wait(&yb[g], aphase);
+        if (store_thread) ptx::tma_store_wait_read<0>();   // the previous tile's output store has left sOut
+        ptx::tc_fence_after();
+        {
+            uint32_t acc[16];
+            ptx::tmem_ld_32x16(t_lane + g * BN + h * 16, acc);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+            const float* bias = sBias + h * 16;
+            float v[16];
+            if (p.act == kActSiluTanh) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float hh = fmaf(__uint_as_float(acc[j]), 0.5f, bias[j]);
+                    v[j] = fmaf(hh, tanh_fast(hh), hh);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    v[j] = __uint_as_float(acc[j]) + bias[j];
+                    if (p.act == WT_ACT_SILU) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                }
+            }
+            uint8_t* rowp = sB8 + row * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                // residual = channels 32 + 16 h + 8 c .. of the cat tile: 16-byte chunk 4 + 2 h + c of its 128-byte row
+                const uint4 r = *reinterpret_cast<const uint4*>(yrow + (((4 + 2 * h + c) ^ (row & 7)) << 4));
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    f[2 * j] = v[8 * c + 2 * j] + __uint_as_float(rw[j] << 16);
+                    f[2 * j + 1] = v[8 * c + 2 * j + 1] + __uint_as_float(rw[j] & 0xFFFF0000u);
+                }
+                uint4 o;
+                o.x = pack_bf16(f[0], f[1]);
+                o.y = pack_bf16(f[2], f[3]);
+                o.z = pack_bf16(f[4], f[5]);
+                o.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4*>(rowp + (((2 * h + c) ^ ((row >> 1) & 3)) << 4)) = o;
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::bar_sync(bar_id, kEpiThreads);
+        if (store_thread) ptx::mbar_arrive(&cb[g]);          // a2_full
+        // ---- pass 1: out = act2(acc2 + bias2)
+        ptx::mbar_wait(&cb[2 + g], aphase);                  // t2full
+        ptx::tc_fence_after();
+        {
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(t_lane + 2 * BN + g * kCatOut + h * 32, acc);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&cb[4 + g]);     // t2empty
+            const float* bias = sBias + BN + h * 32;
+            float v[32];
+            if (p.act2 == kActSiluTanh) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float hh = fmaf(__uint_as_float(acc[j]), 0.5f, bias[j]);
+                    v[j] = fmaf(hh, tanh_fast(hh), hh);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(acc[j]) + bias[j];
+                    if (p.act2 == WT_ACT_SILU) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                }
+            }
+            uint8_t* rowp = sOut + row * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+                o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+                o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+                o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+                *reinterpret_cast<uint4*>(rowp + (((4 * h + c) ^ (row & 7)) << 4)) = o;
+            }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::bar_sync(bar_id, kEpiThreads);
+        if (store_thread) {
+            ptx::tma_store_4d(&p.tmD, sOut, p.dst_coff, tc.x0, tc.y0, tc.n0);
+            ptx::tma_store_commit();
+        }
+    }
+    if (store_thread) ptx::tma_store_wait<0>();
+}
+
+// Warp 2, one elected lane: loads the cat tiles one tile ahead and issues the second UMMA chain
+// (4 K slices of the cat tile x W2a + 2 K slices of the b tile x W2b) into accumulator 2 + g.
+__device__ __forceinline__ void conv_cat_issuer(const ConvTcParams& p, const uint8_t* sStageAll, const uint8_t* sY,
+                                                const uint8_t* sW2a, const uint8_t* sW2b, uint64_t* cb, uint64_t* yb,
+                                                uint64_t* w2_full, uint32_t tmem_base) {
+    constexpr int BN = 32;
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, kCatOut);
+    const int first = blockIdx.x, step = gridDim.x;
+    const uint64_t ba = ptx::make_kmajor_desc<128>(ptx::smem_u32(sW2a));
+    const uint64_t bb = ptx::make_kmajor_desc<64>(ptx::smem_u32(sW2b));
+    ptx::prefetch_tmap(&p.tmY);
+    ptx::grid_dependency_wait();           // the cat buffer is written by earlier kernels
+    if (first < p.num_tiles) {
+        const TileCoord tc = decode_tile<1>(p, first, 0);
+        ptx::mbar_expect_tx(&yb[0], kStageBufBytes);
+        ptx::tma_load_4d(const_cast<uint8_t*>(sY), &p.tmY, &yb[0], p.cat_coff, tc.x0, tc.y0, tc.n0);
+    }
+    ptx::mbar_wait(w2_full, 0);
+    int it = 0;
+    for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+        const int g = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        if (tile + step < p.num_tiles) {   // next tile's cat tile into the other buffer, once its previous user is done
+            if (it >= 1) ptx::mbar_wait(&cb[2 + (g ^ 1)], ((it - 1) >> 1) & 1);   // t2full of tile it - 1
+            const TileCoord tn = decode_tile<1>(p, tile + step, 0);
+            ptx::mbar_expect_tx(&yb[g ^ 1], kStageBufBytes);
+            ptx::tma_load_4d(const_cast<uint8_t*>(sY) + (g ^ 1) * kStageBufBytes, &p.tmY, &yb[g ^ 1], p.cat_coff, tn.x0,
+                             tn.y0, tn.n0);
+        }
+        ptx::mbar_wait(&cb[4 + g], ph ^ 1);   // t2empty
+        ptx::mbar_wait(&yb[g], ph);           // cat tile landed
+        ptx::mbar_wait(&cb[g], ph);           // a2_full: b tile staged
+        ptx::tc_fence_after();
+        const uint64_t ay = ptx::make_kmajor_desc<128>(ptx::smem_u32(sY + g * kStageBufBytes));
+        const uint64_t ab = ptx::make_kmajor_desc<64>(ptx::smem_u32(sStageAll + g * 2 * kStageBufBytes));
+        const uint32_t d_tmem = tmem_base + 2 * BN + g * kCatOut;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            ptx::umma_bf16_lohi(d_tmem, uint32_t(ay) + 2 * kk, uint32_t(ay >> 32), uint32_t(ba) + 2 * kk, uint32_t(ba >> 32),
+                                idesc, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+            ptx::umma_bf16_lohi(d_tmem, uint32_t(ab) + 2 * kk, uint32_t(ab >> 32), uint32_t(bb) + 2 * kk, uint32_t(bb >> 32),
+                                idesc, true);
+        ptx::umma_commit(&cb[2 + g]);         // t2full
+    }
+}
+
 template <int BN, int CG>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
@@ -692,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
     }
 
-    if (warp == 2 && p.chain) {
+    if (warp == 2 && p.chain == 1) {
         // ------------------------------------------------------------------ second UMMA chain (chained 1x1 conv)
         if constexpr ((BN == 64 || BN == 128) && CG == 1) {
             if (ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
@@ -707,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         // The whole warp walks the loop (uniform control flow); one elected lane issues the copies.
-        if (p.chain && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
+        if (p.chain == 1 && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
             ptx::prefetch_tmap(&p.tmB2);
             ptx::mbar_expect_tx(w2_full, BN * BN * 2);
             for (int kb = 0; kb < BN / 64; ++kb)
@@ -887,7 +1070,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint8_t* sB = smem + kAStages * kHaloABytes;               // [kBStages][BN][64] bf16
     uint8_t* sStage = sB + kBStages * L::kBBytes;
     const uint8_t* sW2 = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;   // chained form: W2 [BN / 64][BN][64] bf16
-    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sW2) + (p.chain ? BN * BN * 2 : 0));
+    // concat chain: Y[2] cat tiles, then W2a [64][64] (128-byte rows), then W2b [64][32] (64-byte rows)
+    const uint8_t* sY = sW2;
+    const uint8_t* sW2a = sY + 2 * kStageBufBytes;
+    const uint8_t* sW2b = sW2a + kCatOut * kCatC * 2;
+    float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sW2) +
+                                            (p.chain == 2 ? kCatSmemBytes : (p.chain ? BN * BN * 2 : 0)));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kMaxCout);
     uint64_t* afull = bars;
     uint64_t* aempty = afull + kMaxAStages;
@@ -898,7 +1086,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint64_t* res_bar = tempty_bar + 2;
     uint64_t* chain_bars = res_bar + 4;   // [6] a2_full[2], t2full[2], t2empty[2] (chained form)
     uint64_t* w2_full = res_bar + 10;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 11);
+    uint64_t* y_full = res_bar + 11;      // [2] cat tile TMA -> epilogue group / second MMA chain (concat chain)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 13);
+    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -925,6 +1115,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
         ptx::mbar_init(w2_full, 1);
+        ptx::mbar_init(&y_full[0], 1);
+        ptx::mbar_init(&y_full[1], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -932,7 +1124,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
             ptx::tmem_relinquish_cg2();
         } else {
-            ptx::tmem_alloc(tmem_slot, p.chain ? 4u * BN : kTmemCols);
+            ptx::tmem_alloc(tmem_slot, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
             ptx::tmem_relinquish();
         }
     }
@@ -945,7 +1137,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         for (int i = threadIdx.x; i <= p.cout; i += kThreads) sBias[p.cout + i] = __ldg(p.dot_w + i);
     if (p.chain) {   // bias of the chained 1x1 conv behind the conv bias
         const float bscale2 = p.act2 == kActSiluTanh ? 0.5f : 1.0f;
-        for (int i = threadIdx.x; i < p.cout; i += kThreads) sBias[p.cout + i] = bscale2 * __ldg(p.bias2 + i);
+        const int n2 = p.chain == 2 ? kCatOut : p.cout;
+        for (int i = threadIdx.x; i < n2; i += kThreads) sBias[p.cout + i] = bscale2 * __ldg(p.bias2 + i);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -960,18 +1153,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     if (warp == 2 && p.chain) {
         // second UMMA chain of the chained 1x1 conv
         if constexpr ((BN == 64 || BN == 128) && CG == 1) {
-            if (ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+            if (p.chain == 1 && ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+        }
+        if constexpr (kCatCapable) {
+            if (p.chain == 2 && ptx::elect_one())
+                conv_cat_issuer(p, sStage, sY, sW2a, sW2b, chain_bars, y_full, w2_full, tmem_base);
         }
         __syncwarp();
     }
 
     if (warp == 0) {
         // TMA producer: warp-uniform loop, one elected lane issues
-        if (p.chain && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
+        if (p.chain == 1 && ptx::elect_one()) {   // W2 is a constant: loaded before the grid dependency resolves
             ptx::prefetch_tmap(&p.tmB2);
             ptx::mbar_expect_tx(w2_full, BN * BN * 2);
             for (int kb = 0; kb < BN / 64; ++kb)
                 ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
+        }
+        if (p.chain == 2 && ptx::elect_one()) {
+            ptx::prefetch_tmap(&p.tmB2);
+            ptx::prefetch_tmap(&p.tmB2b);
+            ptx::mbar_expect_tx(w2_full, kCatOut * (kCatC + 32) * 2);
+            ptx::tma_load_2d(const_cast<uint8_t*>(sW2a), &p.tmB2, w2_full, 0, 0);
+            ptx::tma_load_2d(const_cast<uint8_t*>(sW2b), &p.tmB2b, w2_full, kCatC, 0);
         }
         __syncwarp();
         ptx::grid_dependency_wait();
@@ -1139,8 +1343,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         __syncwarp();
     } else {
-        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
-                              nullptr, nullptr, chain_bars);
+        if constexpr (kCatCapable) {
+            if (p.chain == 2)
+                conv_epilogue_cat(p, sStage, sY, sBias, tfull_bar, tempty_bar, chain_bars, y_full, tmem_base, warp, lane);
+        }
+        if (p.chain != 2)
+            conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
+                                  nullptr, nullptr, chain_bars);
     }
 
     ptx::tc_fence_before();
@@ -1149,7 +1358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     if (warp == 1) {
         ptx::tc_fence_after();
         if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
-        else ptx::tmem_dealloc(tmem_base, p.chain ? 4u * BN : kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
     }
 }
 
@@ -1196,7 +1405,8 @@ static int pick_bn(int cout, long long m_tiles, int sm_count, bool allow_192) {
         if (cout % bn != 0 || (bn == 192 && !allow_192)) continue;
         const long long tiles = m_tiles * (cout / bn);
         const long long waves = (tiles + sm_count - 1) / sm_count;
-        const long long cost = waves * (bn + 32);   // per-tile time ~ N plus a fixed part
+        static const int fixed_env = getenv("WT_BN_FIXED") ? atoi(getenv("WT_BN_FIXED")) : 32;   // A/B knob
+        const long long cost = waves * (bn + fixed_env);   // per-tile time ~ N plus a fixed part
         if (best == 0 || cost < best_cost) {
             best = bn;
             best_cost = cost;
@@ -1231,7 +1441,21 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     int bn = d.dot_w ? (d.cout <= 256 && d.cout % 32 == 0 ? d.cout : 0)
                      : pick_bn(d.cout, m_tiles, sm_count, d.cin % 64 == 0 && !halo_s2 && !d.add.base);
     if (d.add.base && bn > 128) bn = 128;   // the addend patch buffers (N x 128 B per epilogue group) stay small
-    if (d.chain_w) {
+    const bool cat_chain = d.chain_w && d.cat.base;
+    if (cat_chain) {
+        // concat chain (C2f exit): 3x3 / stride 1, 32 -> 32 channels with the residual y1 = upper half of the 64-channel
+        // cat slice, then a 1x1 conv over concat(cat slice, output) -> 64 channels
+        WT_REQUIRE(halo_shape && !halo_s2 && d.cin == 32 && d.cout == 32 && d.cat_c == kCatC && d.chain_cout == kCatOut,
+                   "a concat chain is a 32 -> 32 3x3 conv followed by a (64 + 32) -> 64 1x1 conv");
+        WT_REQUIRE(d.res.base == d.cat.base && d.res.coff == d.cat.coff + 32 && d.res.ctot == d.cat.ctot &&
+                       d.cat.h == ho && d.cat.w == wo && d.cat.dtype == WT_DT_BF16,
+                   "the residual of a concat chain is the upper half of its cat slice");
+        WT_REQUIRE(!d.add.base && !d.dot_w && d.dst.dtype == WT_DT_BF16 && (d.cat.ctot * 2) % 16 == 0 &&
+                       (d.cat.coff * 2) % 16 == 0,
+                   "a concat chain has no addend / dot head and writes bf16");
+        bn = 32;
+    } else if (d.chain_w) {
+        WT_REQUIRE(d.chain_cout == 0 || d.chain_cout == d.cout, "a chained 1x1 conv keeps the channel count");
         WT_REQUIRE(d.cout == 64 || d.cout == 128, "a chained 1x1 conv needs 64 or 128 channels (one N tile, 4 accumulators)");
         WT_REQUIRE(!d.res.base && !d.add.base && !d.dot_w && d.dst.dtype == WT_DT_BF16,
                    "a chained conv has no residual / addend / dot head and writes bf16");
@@ -1297,13 +1521,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.res_coff = d.res.base ? d.res.coff : 0;
     static const int silu_exact = getenv("WT_SILU_EXACT") ? atoi(getenv("WT_SILU_EXACT")) : 0;
     p.act = (d.act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : d.act;
-    p.has_res = d.res.base ? 1 : 0;
+    p.has_res = (d.res.base && !cat_chain) ? 1 : 0;   // concat chain: the residual is read from the cat tile in smem
     p.out_f32 = out_f32 ? 1 : 0;
     p.bias = d.bias;
     p.has_add = d.add.base ? 1 : 0;
     p.add_coff = d.add.coff;
     p.dot_w = d.dot_w;
-    p.chain = d.chain_w ? 1 : 0;
+    p.chain = cat_chain ? 2 : (d.chain_w ? 1 : 0);
+    p.cat_coff = cat_chain ? d.cat.coff : 0;
     p.bias2 = d.chain_bias;
     p.act2 = (d.chain_act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : d.chain_act;
     p.dot_out = d.dot_w ? static_cast<float*>(d.dst.base) : nullptr;
@@ -1317,7 +1542,9 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     static const int epi_env = getenv("WT_EPI_BUFS") ? atoi(getenv("WT_EPI_BUFS")) : 0;   // A/B knob: 1 | 2 everywhere
     if (epi_env == 1 || epi_env == 2) p.epi_bufs = epi_env;
     if (d.chain_w) p.epi_bufs = bn / 64;   // the staging buffers of a group hold the whole bf16 tile (A of the second GEMM)
-    const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) + (d.chain_w ? bn * bn * 2 : 0);
+    if (cat_chain) p.epi_bufs = 2;         // b tile + output tile
+    const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) +
+                      (cat_chain ? kCatSmemBytes : (d.chain_w ? bn * bn * 2 : 0));
     if (pl->halo) {
         p.a_stages = bn == 256 ? 2 : 3;
         const int b_bytes = (bn / cg) * bk * 2;
@@ -1405,7 +1632,23 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
                           sw_in);
     }
     p.tmB2 = p.tmB;
-    if (d.chain_w) {   // W2 [cout][cout] bf16, K-major rows; one box = 64 input channels of every output channel
+    p.tmB2b = p.tmB;
+    p.tmY = p.tmA[0];
+    if (cat_chain) {
+        // W2 [64][96] bf16: K block 0 = 64 channels (128-byte rows), K block 1 = 32 channels (64-byte rows)
+        const uint64_t dims[2] = {uint64_t(kCatC + 32), uint64_t(kCatOut)};
+        const uint64_t str[1] = {uint64_t(kCatC + 32) * 2};
+        const uint32_t box_a[2] = {uint32_t(kCatC), uint32_t(kCatOut)}, box_b[2] = {32, uint32_t(kCatOut)};
+        rc |= encode_tmap(&p.tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.chain_w), dims, str,
+                          box_a, 128);
+        rc |= encode_tmap(&p.tmB2b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.chain_w), dims, str,
+                          box_b, 64);
+        // the cat tile of a 16 x 8 pixel patch: 64 channels = one 128-byte row per pixel
+        const uint64_t ydims[4] = {uint64_t(d.cat.coff + kCatC), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
+        const uint64_t ystr[3] = {uint64_t(d.cat.ctot) * 2, uint64_t(d.cat.ctot) * 2 * wo, uint64_t(d.cat.ctot) * 2 * wo * ho};
+        const uint32_t ybox[4] = {uint32_t(kCatC), 8, 16, 1};
+        rc |= encode_tmap(&p.tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.cat.base, ydims, ystr, ybox, 128);
+    } else if (d.chain_w) {   // W2 [cout][cout] bf16, K-major rows; one box = 64 input channels of every output channel
         const uint64_t dims[2] = {uint64_t(d.cout), uint64_t(d.cout)};
         const uint64_t str[1] = {uint64_t(d.cout) * 2};
         const uint32_t box[2] = {64, uint32_t(d.cout)};
@@ -1431,7 +1674,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         p.tmR = p.tmA[0];
     } else {
         const int es = out_f32 ? 4 : 2;
-        const int unit_ch = out_f32 ? 32 : (bn == 32 ? 32 : 64);
+        const int unit_ch = out_f32 ? 32 : ((bn == 32 && !cat_chain) ? 32 : 64);   // (concat chain: 64 output channels)
         const int sw = unit_ch * es;   // 128 or 64
         const uint64_t dims[4] = {uint64_t(d.dst.ctot), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
         const uint64_t str[3] = {uint64_t(d.dst.ctot) * es, uint64_t(d.dst.ctot) * es * wo,

@@ -86,8 +86,9 @@ void op_ranges(const wt_op& o, std::vector<ChanRange>& rd, std::vector<ChanRange
             rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
             if (o.res >= 0) rd.push_back({o.res, o.res_coff, o.res_coff + o.cout});
             if (o.add_buf >= 0) rd.push_back({o.add_buf, o.add_coff, o.add_coff + o.cout});
+            if (o.chain_w_off >= 0 && o.cat_buf >= 0) rd.push_back({o.cat_buf, o.cat_coff, o.cat_coff + o.cat_c});
             if (o.dot_off >= 0) wr.push_back({o.dst, 0, 1});
-            else wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cout});
+            else wr.push_back({o.dst, o.dst_coff, o.dst_coff + ((o.chain_w_off >= 0 && o.cat_buf >= 0) ? o.chain_cout : o.cout)});
             break;
         case WT_OP_CONV0:
             rd.push_back({o.src, 0, 1});
@@ -182,10 +183,22 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             d.chain_w = nullptr;
             d.chain_bias = nullptr;
             d.chain_act = 0;
+            d.cat = TensorView{nullptr, 0, 0, 0, 0, 0};
+            d.cat_c = 0;
+            d.chain_cout = 0;
             if (o.chain_w_off >= 0) {
+                const bool cat = o.cat_buf >= 0;
+                const int64_t c2 = cat ? o.chain_cout : o.cout, k2 = cat ? int64_t(o.cat_c) + o.cout : o.cout;
+                if (cat) {
+                    if (o.cat_buf >= n_bufs || o.cat_c <= 0 || o.chain_cout <= 0 || o.cat_coff < 0 ||
+                        o.cat_coff + o.cat_c > e->bufs[o.cat_buf].c)
+                        return fail("concat-chain slice out of range", i);
+                    d.cat = view_of(e, o.cat_buf, o.cat_coff);
+                    d.cat_c = o.cat_c;
+                    d.chain_cout = o.chain_cout;
+                }
                 if (o.chain_w_off % 16 != 0 || o.chain_b_off < 0 || o.chain_b_off % 4 != 0 ||
-                    o.chain_w_off + int64_t(o.cout) * o.cout * 2 > weight_bytes ||
-                    o.chain_b_off + int64_t(o.cout) * 4 > weight_bytes)
+                    o.chain_w_off + c2 * k2 * 2 > weight_bytes || o.chain_b_off + c2 * 4 > weight_bytes)
                     return fail("chained conv weights out of range", i);
                 if (conv_impl != 0) return fail("chained convs exist on the tcgen05 path only", i);
                 d.chain_w = reinterpret_cast<const __nv_bfloat16*>(e->weights + o.chain_w_off);
@@ -193,7 +206,8 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
                 d.chain_act = o.chain_act;
             }
             d.batch = batch;
-            if (o.src_coff + o.cin > e->bufs[o.src].c || (!d.dot_w && o.dst_coff + o.cout > e->bufs[o.dst].c))
+            if (o.src_coff + o.cin > e->bufs[o.src].c ||
+                (!d.dot_w && o.dst_coff + (d.cat.base ? d.chain_cout : o.cout) > e->bufs[o.dst].c))
                 return fail("channel slice exceeds buffer", i);
             if (conv_impl == 0) {
                 if (conv_tc_plan_create(d, &e->conv_plan[i])) {
@@ -365,6 +379,7 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     d.cin = cin; d.cout = cout; d.k = k; d.stride = stride; d.act = act;
     d.w = d_w; d.bias = d_bias; d.dot_w = nullptr; d.batch = batch;
     d.chain_w = nullptr; d.chain_bias = nullptr; d.chain_act = 0;
+    d.cat = TensorView{nullptr, 0, 0, 0, 0, 0}; d.cat_c = 0; d.chain_cout = 0;
     ConvTcPlan* plan = nullptr;
     int rc = conv_tc_plan_create(d, &plan);
     if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);
@@ -426,6 +441,7 @@ extern "C" int wt_selftest_conv_chain(int batch, int h, int w, int cin, int cout
     a.cin = cin; a.cout = cout; a.k = k; a.stride = stride; a.act = WT_ACT_SILU;
     a.w = d_w; a.bias = d_bias; a.dot_w = nullptr; a.batch = batch;
     a.chain_w = nullptr; a.chain_bias = nullptr; a.chain_act = 0;
+    a.cat = TensorView{nullptr, 0, 0, 0, 0, 0}; a.cat_c = 0; a.chain_cout = 0;
     ConvDesc b = a;   // the 1x1 conv on the intermediate buffer
     b.src = a.dst;
     b.dst = TensorView{d_ref, ho, wo, dst_ct, dst_off, WT_DT_BF16};
@@ -454,5 +470,75 @@ extern "C" int wt_selftest_conv_chain(int batch, int h, int w, int cin, int cout
     if (verbose)
         printf("selftest_conv_chain b%d %dx%d cin%d cout%d k%d s%d : max|diff| %.5g (ref max %.4g)\n", batch, h, w, cin, cout,
                k, stride, stats[0], stats[1]);
+    return 0;
+}
+
+extern "C" int wt_selftest_conv_cat(int batch, int h, int w, int verbose, double* max_abs_diff) {
+    // C2f exit: b = y1 + SiLU(conv3x3(b1)); out = SiLU(W2 * [y0 | y1 | b] + b2), as ONE concat-chain launch and as two
+    // tcgen05 launches through the concat buffer; the results must be identical.
+    int sm = 0, cc = 0;
+    if (wt_device_info(&sm, &cc, nullptr)) return 1;
+    const int c = 32, cat_ct = 3 * c, out_ct = 2 * c + 64, out_off = 32;
+    const size_t n_px = size_t(batch) * h * w;
+    const size_t n_cat = n_px * cat_ct, n_b1 = n_px * c, n_out = n_px * out_ct, n_w = size_t(c) * 9 * c, n_w2 = size_t(2 * c) * cat_ct;
+    __nv_bfloat16 *d_cat = nullptr, *d_b1 = nullptr, *d_w = nullptr, *d_w2 = nullptr, *d_out = nullptr, *d_ref = nullptr;
+    float *d_bias = nullptr, *d_bias2 = nullptr, *d_stats = nullptr;
+    WT_CHECK_CUDA(cudaMalloc(&d_cat, n_cat * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_b1, n_b1 * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_w, n_w * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_w2, n_w2 * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_out, n_out * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_ref, n_out * 2));
+    WT_CHECK_CUDA(cudaMalloc(&d_bias, c * 4));
+    WT_CHECK_CUDA(cudaMalloc(&d_bias2, 2 * c * 4));
+    WT_CHECK_CUDA(cudaMalloc(&d_stats, 8));
+    WT_CHECK_CUDA(cudaMemset(d_out, 0, n_out * 2));
+    WT_CHECK_CUDA(cudaMemset(d_ref, 0, n_out * 2));
+    WT_CHECK_CUDA(cudaMemset(d_stats, 0, 8));
+    fill_bf16<<<unsigned((n_cat + 255) / 256), 256>>>(d_cat, n_cat, 1u, 1.0f);
+    fill_bf16<<<unsigned((n_b1 + 255) / 256), 256>>>(d_b1, n_b1, 7u, 1.0f);
+    fill_bf16<<<unsigned((n_w + 255) / 256), 256>>>(d_w, n_w, 2u, 1.0f / sqrtf(float(9 * c)));
+    fill_bf16<<<unsigned((n_w2 + 255) / 256), 256>>>(d_w2, n_w2, 5u, 2.0f / sqrtf(float(cat_ct)));
+    fill_f32<<<1, 256>>>(d_bias, c, 4u, 0.5f);
+    fill_f32<<<1, 256>>>(d_bias2, 2 * c, 6u, 0.5f);
+    const TensorView none{nullptr, 0, 0, 0, 0, 0};
+    ConvDesc a;   // the bottleneck's second conv into the third slice of the concat buffer, residual = second slice
+    a.src = TensorView{d_b1, h, w, c, 0, WT_DT_BF16};
+    a.dst = TensorView{d_cat, h, w, cat_ct, 2 * c, WT_DT_BF16};
+    a.res = TensorView{d_cat, h, w, cat_ct, c, WT_DT_BF16};
+    a.add = none; a.cat = none; a.cat_c = 0; a.chain_cout = 0;
+    a.cin = c; a.cout = c; a.k = 3; a.stride = 1; a.act = WT_ACT_SILU;
+    a.w = d_w; a.bias = d_bias; a.dot_w = nullptr; a.batch = batch;
+    a.chain_w = nullptr; a.chain_bias = nullptr; a.chain_act = 0;
+    ConvDesc b = a;   // cv2 over the whole concat buffer
+    b.src = TensorView{d_cat, h, w, cat_ct, 0, WT_DT_BF16};
+    b.dst = TensorView{d_ref, h, w, out_ct, out_off, WT_DT_BF16};
+    b.res = none;
+    b.cin = cat_ct; b.cout = 2 * c; b.k = 1; b.w = d_w2; b.bias = d_bias2;
+    ConvDesc f = a;   // both in one launch; the third slice of the concat buffer is not written
+    f.dst = TensorView{d_out, h, w, out_ct, out_off, WT_DT_BF16};
+    f.cat = TensorView{d_cat, h, w, cat_ct, 0, WT_DT_BF16};
+    f.cat_c = 2 * c; f.chain_cout = 2 * c;
+    f.chain_w = d_w2; f.chain_bias = d_bias2; f.chain_act = WT_ACT_SILU;
+    int rc = 0;
+    for (const ConvDesc* d : {&f, &a, &b}) {   // the fused launch first: it must not depend on slice 3 being written
+        ConvTcPlan* plan = nullptr;
+        if (!rc) rc = conv_tc_plan_create(*d, &plan);
+        if (!rc) rc = conv_tc_launch(plan, batch, sm, 0);
+        if (plan) conv_tc_plan_destroy(plan);
+    }
+    float stats[2] = {0, 0};
+    if (!rc) {
+        max_diff_kernel<<<unsigned((n_out + 255) / 256), 256>>>(d_out, d_ref, n_out, 0, d_stats, d_stats + 1);
+        cudaError_t e1 = cudaDeviceSynchronize();
+        if (e1 != cudaSuccess) { set_error(std::string("selftest kernel failed: ") + cudaGetErrorString(e1)); rc = 1; }
+        else cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_cat); cudaFree(d_b1); cudaFree(d_w); cudaFree(d_w2); cudaFree(d_out); cudaFree(d_ref);
+    cudaFree(d_bias); cudaFree(d_bias2); cudaFree(d_stats);
+    if (rc) return rc;
+    if (max_abs_diff) *max_abs_diff = stats[0];
+    if (verbose)
+        printf("selftest_conv_cat b%d %dx%d : max|diff| %.5g (ref max %.4g)\n", batch, h, w, stats[0], stats[1]);
     return 0;
 }

@@ -56,10 +56,14 @@ def _align(blob: bytearray, a: int) -> int:
     return len(blob)
 
 
-def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net_w: int, chain: bool = True) -> Program:
+def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net_w: int, chain: bool = True,
+                  chain_exit: bool | None = None) -> Program:
     """``chain``: chain C2f.cv1 onto the stride-2 conv before it where the engine supports it (wt_op.chain_w_off;
     tcgen05 path only, so the scalar validation engine is built with chain=False)."""
     assert net_h % 32 == 0 and net_w % 32 == 0, "network input must be a multiple of 32"
+    if chain_exit is None:        # the C2f-exit concat chain follows `chain` unless switched off (WT_CHAIN_EXIT=0)
+        import os
+        chain_exit = chain and os.environ.get("WT_CHAIN_EXIT", "1") != "0"
     assert arch.nc == 1, "the fused class-logit path is written for single-class models (reference: single_cls)"
     p = Program(arch, net_h, net_w)
     specs = {s.name: s for s in arch.conv_specs()}
@@ -171,9 +175,25 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
                                     down)
         else:
             conv(f"model.{idx}.cv1", src, (cat, 0))
+        s2 = specs[f"model.{idx}.cv2"]
+        cat_chain = (chain_exit and spec.n == 1 and cc == 32 and spec.shortcut and s2.k == 1 and s2.cin == 3 * cc
+                     and s2.cout == 2 * cc and net_h % 64 == 0 and net_w % 32 == 0)
         for i in range(spec.n):
             x_in = (cat, (1 + i) * cc)
             conv(f"model.{idx}.m.{i}.cv1", x_in, (tmp, 0))
+            if cat_chain:
+                # exit of the block as one launch (wt_op.cat_buf): b = y1 + act(conv3x3(tmp)) stays in shared memory and
+                # cv2 runs over [y0 | y1 | b] right there; the third slice of the concat buffer is never written
+                conv(f"model.{idx}.m.{i}.cv2", (tmp, 0), dst, res=x_in)
+                w2, b2 = folded_conv(sd, s2)
+                w2_off = _align(p.blob, 16)
+                p.blob.extend(w2.reshape(s2.cout, s2.cin).contiguous().to(torch.bfloat16).view(torch.int16).numpy().tobytes())
+                b2_off = _align(p.blob, 16)
+                p.blob.extend(b2.float().numpy().tobytes())
+                p.ops[-1].update(name=f"model.{idx}.m.{i}.cv2>model.{idx}.cv2", chain_w_off=w2_off, chain_b_off=b2_off,
+                                 chain_act=L.WT_ACT_SILU if s2.bn_act else L.WT_ACT_NONE, cat_buf=cat, cat_coff=0,
+                                 cat_c=2 * cc, chain_cout=s2.cout)
+                return
             conv(f"model.{idx}.m.{i}.cv2", (tmp, 0), (cat, (2 + i) * cc), res=x_in if spec.shortcut else None)
         conv(f"model.{idx}.cv2", (cat, 0), dst)
 
@@ -296,7 +316,8 @@ def ops_as_ctypes(p: Program):
     for i, o in enumerate(p.ops):
         ops[i] = L.WtOp(o["kind"], o["src"], o["src_coff"], o["dst"], o["dst_coff"], o["res"], o["res_coff"],
                         o["cin"], o["cout"], o["k"], o["stride"], o["act"], o["w_off"], o["b_off"], o.get("dot_off", -1), o.get("add_buf", -1), o.get("add_coff", 0),
-                        o.get("lane", 0), o.get("chain_act", 0), o.get("chain_w_off", -1), o.get("chain_b_off", -1))
+                        o.get("lane", 0), o.get("chain_act", 0), o.get("chain_w_off", -1), o.get("chain_b_off", -1),
+                        o.get("cat_buf", -1), o.get("cat_coff", 0), o.get("cat_c", 0), o.get("chain_cout", 0))
     return bufs, ops
 
 
