@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(kConv0Threads, 4) conv0_px2_kernel(const uint8
 // whole grid is resident at once: the kernel is a chain of six barrier-separated passes, i.e. latency-bound.
 constexpr int kPoolCg = 8;
 constexpr int kPoolThreads = 128;
+constexpr int kPoolIter = 4;          // pixels per thread: feature maps up to 512 pixels (20x20 at 640, 12x12 at 384)
 
 __device__ __forceinline__ uint4 max_bf16x8(const uint4 a, const uint4 b) {
     uint4 r;
@@ -383,13 +384,70 @@ __device__ __forceinline__ uint4 max_bf16x8(const uint4 a, const uint4 b) {
     return r;
 }
 
-__global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, int sct,
-                                                                 int scoff, __nv_bfloat16* __restrict__ dst, int dct,
-                                                                 int dcoff, int c, int h, int w) {
+// G channel groups (8 channels = one 16-byte word each) per CTA, thread = (pixel lane, group): the G words of a pixel
+// are contiguous in global memory (full 32-byte sectors instead of half ones), and at G = 4 the whole grid (c / 32
+// x images CTAs of 512 threads) is resident in ONE wave on 148 SMs — with G = 1 the last 15 % of the CTAs cost a second
+// round of this latency-bound chain.
+template <int G>
+__global__ void __launch_bounds__(kPoolThreads * G) sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, int sct,
+                                                                     int scoff, __nv_bfloat16* __restrict__ dst, int dct,
+                                                                     int dcoff, int c, int h, int w) {
     extern __shared__ uint4 pool_smem[];
     const int hw = h * w;
-    uint4* cur = pool_smem;          // [hw]
-    uint4* tmp = pool_smem + hw;     // [hw]
+    uint4* cur = pool_smem;              // [hw][G]
+    uint4* tmp = pool_smem + hw * G;     // [hw][G]
+    const int n = blockIdx.y;
+    const int g = threadIdx.x % G, lane_px = threadIdx.x / G;
+    const int c0 = (blockIdx.x * G + g) * kPoolCg;
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    for (int i = lane_px; i < hw; i += kPoolThreads)
+        cur[i * G + g] = __ldg(reinterpret_cast<const uint4*>(src + (size_t(n) * hw + i) * sct + scoff + c0));
+    // a thread owns at most kPoolIter pixels (hw <= kPoolIter * 128): their coordinates are computed once, not with
+    // a division in every one of the six passes (the kernel is instruction-issue bound at full occupancy)
+    int px[kPoolIter], py[kPoolIter];
+#pragma unroll
+    for (int k = 0; k < kPoolIter; ++k) {
+        const int i = lane_px + k * kPoolThreads;
+        py[k] = i < hw ? i / w : -1000;      // (out-of-range slots fail every tap test below)
+        px[k] = i < hw ? i - py[k] * w : -1000;
+    }
+    __syncthreads();
+    for (int round = 0; round < 3; ++round) {
+#pragma unroll
+        for (int k = 0; k < kPoolIter; ++k) {
+            const int i = lane_px + k * kPoolThreads, x = px[k];
+            if (x < 0) continue;
+            uint4 m = cur[i * G + g];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && x + d >= 0 && x + d < w) m = max_bf16x8(m, cur[(i + d) * G + g]);
+            tmp[i * G + g] = m;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPoolIter; ++k) {
+            const int i = lane_px + k * kPoolThreads, y = py[k];
+            if (y < 0) continue;
+            uint4 m = tmp[i * G + g];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d)
+                if (d != 0 && y + d >= 0 && y + d < h) m = max_bf16x8(m, tmp[(i + d * w) * G + g]);
+            *reinterpret_cast<uint4*>(dst + (size_t(n) * hw + i) * dct + dcoff + round * c + c0) = m;
+            cur[i * G + g] = m;     // only this thread touches element (i, g) before the barrier
+        }
+        __syncthreads();
+    }
+}
+
+// Any map size (one channel group per CTA, coordinates recomputed per pass): used above 512 pixels.
+__global__ void __launch_bounds__(kPoolThreads) sppf_pool_generic_kernel(const __nv_bfloat16* __restrict__ src, int sct,
+                                                                         int scoff, __nv_bfloat16* __restrict__ dst,
+                                                                         int dct, int dcoff, int c, int h, int w) {
+    extern __shared__ uint4 pool_smem[];
+    const int hw = h * w;
+    uint4* cur = pool_smem;
+    uint4* tmp = pool_smem + hw;
     const int n = blockIdx.y;
     const int c0 = blockIdx.x * kPoolCg;
     ptx::grid_launch_dependents();
@@ -414,7 +472,7 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_kernel(const __nv_bflo
             for (int d = -2; d <= 2; ++d)
                 if (d != 0 && y + d >= 0 && y + d < h) m = max_bf16x8(m, tmp[i + d * w]);
             *reinterpret_cast<uint4*>(dst + (size_t(n) * hw + i) * dct + dcoff + round * c + c0) = m;
-            cur[i] = m;     // only this thread touches element i before the barrier
+            cur[i] = m;
         }
         __syncthreads();
     }
@@ -503,16 +561,20 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
                "SPPF channels and slices must be multiples of 8");
     WT_REQUIRE(src.h == dst.h && src.w == dst.w, "SPPF keeps the spatial size");
     WT_REQUIRE(src.dtype == WT_DT_BF16 && dst.dtype == WT_DT_BF16, "SPPF works on bf16");
-    const size_t smem = size_t(src.h) * src.w * sizeof(uint4) * 2;
+    const bool small = src.h * src.w <= kPoolIter * kPoolThreads;
+    const int G = (small && c % (4 * kPoolCg) == 0) ? 4 : 1;
+    const size_t smem = size_t(src.h) * src.w * sizeof(uint4) * 2 * G;
     WT_REQUIRE(smem <= 200 * 1024, "SPPF feature map too large for the shared-memory pool kernel");
     if (n_images == 0) return 0;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
+    auto* kernel = !small ? sppf_pool_generic_kernel : (G == 4 ? sppf_pool_kernel<4> : sppf_pool_kernel<1>);
+    static size_t configured[3] = {0, 0, 0};
+    const int slot = !small ? 2 : (G == 4);
+    if (smem > 48 * 1024 && smem > configured[slot]) {
+        WT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured[slot] = smem;
     }
-    dim3 grid(c / kPoolCg, n_images);
-    WT_CHECK_CUDA(launch_pdl(sppf_pool_kernel, grid, dim3(kPoolThreads), smem, stream,
+    dim3 grid(c / (kPoolCg * G), n_images);
+    WT_CHECK_CUDA(launch_pdl(kernel, grid, dim3(kPoolThreads * G), smem, stream,
                              static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
                              static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w));
     WT_LAUNCHED();
