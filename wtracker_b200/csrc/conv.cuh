@@ -37,6 +37,10 @@ struct ConvTcPlan;   // opaque: tensor maps + tiling, built once per layer
 int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out);
 void conv_tc_plan_destroy(ConvTcPlan* p);
 int conv_tc_launch(const ConvTcPlan* p, int n_images, int sm_count, cudaStream_t stream);
+// first layer on the tensor cores: wmat = bf16 [32][32] (hi taps | 0 | lo taps | 0 per output channel); launched with
+// conv_tc_launch like every other plan
+int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* wmat, const float* bias, int act,
+                         const TensorView& dst, int batch, ConvTcPlan** out);
 
 // ---- scalar validation path ---------------------------------------------------------------
 int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream);

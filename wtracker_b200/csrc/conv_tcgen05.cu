@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace wt {
 
@@ -87,6 +88,8 @@ struct ConvTcParams {
     // SWIZZLE_128B) + a 32-channel K block (tmB2b, SWIZZLE_64B like the staging tile it multiplies).
     CUtensorMap tmY, tmB2b;
     int cat_coff;
+    // first layer on the tensor cores (conv0_tc_kernel): u8 grey input map [n][in_h][in_w]
+    CUtensorMap tmIn;
     // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
     // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
     // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
@@ -1362,6 +1365,256 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// First layer (u8 grey -> 32 channels, 3x3 stride 2) on the tensor cores.  K = 9 taps is one UMMA K step once padded
+// to 16, so the whole main loop of a 128-pixel tile is TWO instructions: the weights are split into bf16 hi + lo parts
+// (w = hi + lo to 2^-17) and the K block is [9 taps | 0 x 7 | the same 9 taps | 0 x 7] against [hi | 0 | lo | 0] —
+// the u8 pixels are exact in bf16, the products exact in the fp32 accumulator.  What the CUDA-core form spends its
+// time on (288 FMAs per 32 outputs) disappears; what remains is bias + SiLU + bf16 + store.  A 128 x 32 tile is far
+// too small a unit of synchronisation (its barriers and index arithmetic cost more than its work), so the unit here
+// is a SUPER-TILE of 64 x 8 output pixels = four UMMA tiles in four 32-column slices of one accumulator buffer:
+//   warp 0      : TMA — the weight matrix once, then per super-tile the raw 17 x 160-byte input patch (out-of-image
+//                 bytes are zero-filled: the conv padding; the inner coordinate is kept 16-byte aligned) through a ring
+//   warp 1      : MMA issuer (eight UMMAs per super-tile)
+//   warps 3..18 : two epilogue groups, one per accumulator buffer: four tcgen05.ld + bias / SiLU / bf16 passes into one
+//                 32 KB staging tile, ONE barrier pair and ONE TMA store (32 ch x 64 x 8 px) per super-tile
+//   warps 19..26: im2col builders: warps 0-3 build sub-tiles 0 and 2, warps 4-7 sub-tiles 1 and 3; thread = output
+//                 pixel, reads its 9 bytes from the raw patch, converts (PRMT + FADD, no XU pipe) and writes its
+//                 64-byte im2col row with the 64-byte swizzle.
+constexpr int kC0Threads = kThreads + 256;
+constexpr int kC0RawW = 160, kC0RawH = 17, kC0RawBytes = 2816, kC0RawX = 16;   // 17 x 160 B = 2720 B per slot (128-byte aligned)
+constexpr int kC0RawStages = 8, kC0AStages = 8;
+constexpr int kC0ABytes = kTileM * 64;                           // im2col tile: 128 rows x 32 bf16
+constexpr int kC0TileW = 64, kC0TileH = 8, kC0Sub = 4;           // super-tile, UMMA tiles per super-tile
+
+__global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_constant__ ConvTcParams p) {
+    constexpr int BN = 32;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* sA = smem;                                            // [kC0AStages][128][64 B]
+    uint8_t* sStage = sA + kC0AStages * kC0ABytes;                 // 2 groups x 32 KB output staging
+    uint8_t* sB = sStage + kEpiGroups * 2 * kStageBufBytes;        // [32][64 B] weights (hi | lo)
+    uint8_t* sRaw = sB + 2048;                                     // [kC0RawStages][2816 B]
+    float* sBias = reinterpret_cast<float*>(sRaw + kC0RawStages * kC0RawBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64);
+    uint64_t* raw_full = bars;                                     // [8] TMA -> builders
+    uint64_t* raw_empty = raw_full + kC0RawStages;                 // [8] builders -> TMA
+    uint64_t* a_full = raw_empty + kC0RawStages;                   // [8] builders -> MMA
+    uint64_t* a_empty = a_full + kC0AStages;                       // [8] MMA -> builders
+    uint64_t* tfull_bar = a_empty + kC0AStages;                    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                          // [2]
+    uint64_t* w_full = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int first = blockIdx.x, step = gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&p.tmIn);
+        ptx::prefetch_tmap(&p.tmB);
+        ptx::prefetch_tmap(&p.tmD);
+        for (int s = 0; s < kC0RawStages; ++s) {
+            ptx::mbar_init(&raw_full[s], 1);
+            ptx::mbar_init(&raw_empty[s], 8);     // the eight builder warps
+        }
+        for (int s = 0; s < kC0AStages; ++s) {
+            ptx::mbar_init(&a_full[s], 4);        // the four builder warps of a sub-tile
+            ptx::mbar_init(&a_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 8);
+        }
+        ptx::mbar_init(w_full, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 2 * kC0Sub * BN);
+        ptx::tmem_relinquish();
+    }
+    {
+        const float bscale = p.act == kActSiluTanh ? 0.5f : 1.0f;
+        for (int i = threadIdx.x; i < BN; i += kC0Threads) sBias[i] = bscale * __ldg(p.bias + i);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ptx::grid_launch_dependents();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA: weights once, raw patches per super-tile
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(w_full, 2048);
+            ptx::tma_load_2d(sB, &p.tmB, w_full, 0, 0);
+        }
+        __syncwarp();
+        ptx::grid_dependency_wait();      // the input image is written by the crop / letterbox kernel
+        int it = 0;
+        for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+            const TileCoord tc = decode_tile<1>(p, tile, 0);
+            const int s = it % kC0RawStages;
+            ptx::mbar_wait(&raw_empty[s], ((it / kC0RawStages) & 1) ^ 1);
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(&raw_full[s], kC0RawW * kC0RawH);
+                ptx::tma_load_3d(sRaw + s * kC0RawBytes, &p.tmIn, &raw_full[s], 2 * tc.x0 - kC0RawX, 2 * tc.y0 - 1, tc.n0);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer: 4 x 2 UMMAs per super-tile
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
+            const uint64_t b_desc = ptx::make_kmajor_desc<64>(ptx::smem_u32(sB));
+            const uint64_t a_desc0 = ptx::make_kmajor_desc<64>(ptx::smem_u32(sA));
+            ptx::mbar_wait(w_full, 0);
+            int it = 0;
+            for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+                const int ab = it & 1;
+                ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
+#pragma unroll
+                for (int j = 0; j < kC0Sub; ++j) {
+                    const int s = (it * kC0Sub + j) % kC0AStages;
+                    ptx::mbar_wait(&a_full[s], ((it * kC0Sub + j) / kC0AStages) & 1);
+                    ptx::tc_fence_after();
+                    const uint32_t a_lo = uint32_t(a_desc0) + s * (kC0ABytes >> 4);
+                    const uint32_t d_tmem = tmem_base + (ab * kC0Sub + j) * BN;
+                    ptx::umma_bf16_lohi(d_tmem, a_lo, uint32_t(a_desc0 >> 32), uint32_t(b_desc), uint32_t(b_desc >> 32), idesc,
+                                        false);
+                    ptx::umma_bf16_lohi(d_tmem, a_lo + 2, uint32_t(a_desc0 >> 32), uint32_t(b_desc) + 2,
+                                        uint32_t(b_desc >> 32), idesc, true);
+                    ptx::umma_commit(&a_empty[s]);
+                }
+                ptx::umma_commit(&tfull_bar[ab]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + 16) {
+        // ------------------------------------------------------------------ epilogue: one accumulator buffer per group
+        const int ew = warp - kFirstEpiWarp;
+        const int g = ew >> 3, h = (ew >> 2) & 1;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool store_thread = (threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads) == 0;
+        uint8_t* stage = sStage + g * 2 * kStageBufBytes;
+        const int bar_id = kEpiBarrier + g;
+        const int xr = (row >> 1) & 3;
+        float bias[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bias[j] = sBias[h * 16 + j];
+        ptx::grid_dependency_wait();
+        int it = g;
+        for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+            const TileCoord tc = decode_tile<1>(p, tile, 0);
+            ptx::mbar_wait(&tfull_bar[g], (it >> 1) & 1);
+            if (store_thread) ptx::tma_store_wait_read<0>();
+            ptx::tc_fence_after();
+            ptx::bar_sync(bar_id, kEpiThreads);
+            const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kC0Sub * BN + h * 16;
+#pragma unroll 2
+            for (int j = 0; j < kC0Sub; ++j) {
+                uint32_t acc[16];
+                ptx::tmem_ld_32x16(t_lane + j * BN, acc);
+                ptx::tmem_ld_wait();
+                if (j == kC0Sub - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[g]);
+                }
+                float v[16];
+                if (p.act == kActSiluTanh) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float hh = fmaf(__uint_as_float(acc[k]), 0.5f, bias[k]);
+                        v[k] = fmaf(hh, tanh_fast(hh), hh);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        v[k] = __uint_as_float(acc[k]) + bias[k];
+                        if (p.act == WT_ACT_SILU) v[k] = __fdividef(v[k], 1.0f + __expf(-v[k]));
+                    }
+                }
+                uint8_t* rowp = stage + j * kC0ABytes + row * 64;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint4 o;
+                    o.x = pack_bf16(v[8 * c + 0], v[8 * c + 1]);
+                    o.y = pack_bf16(v[8 * c + 2], v[8 * c + 3]);
+                    o.z = pack_bf16(v[8 * c + 4], v[8 * c + 5]);
+                    o.w = pack_bf16(v[8 * c + 6], v[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(rowp + (((2 * h + c) ^ xr) << 4)) = o;
+                }
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::bar_sync(bar_id, kEpiThreads);
+            if (store_thread) {
+                ptx::tma_store_4d(&p.tmD, stage, p.dst_coff, tc.x0, tc.y0, tc.n0);
+                ptx::tma_store_commit();
+            }
+        }
+        if (store_thread) ptx::tma_store_wait<0>();
+    } else if (warp >= kFirstEpiWarp + 16) {
+        // ------------------------------------------------------------------ im2col builders
+        const int bw = warp - (kFirstEpiWarp + 16);          // 0..7
+        const int r = (bw & 3) * 32 + lane;                  // pixel of a UMMA tile == accumulator row
+        const int lx = r % kC0TileW;
+        const int xr = (r >> 1) & 3;
+        const uint32_t zero = 0u;
+        int it = 0;
+        for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
+            const int rs = it % kC0RawStages;
+            ptx::mbar_wait(&raw_full[rs], (it / kC0RawStages) & 1);
+            uint32_t v[2][9];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int j = (bw >> 2) + 2 * k;                             // sub-tile of this warp in round k
+                const int ly = 2 * j + r / kC0TileW;                         // output row inside the super-tile
+                const uint8_t* raw = sRaw + rs * kC0RawBytes + (2 * ly) * kC0RawW + 2 * lx + (kC0RawX - 1);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) v[k][kh * 3 + kw] = raw[kh * kC0RawW + kw];
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&raw_empty[rs]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int j = (bw >> 2) + 2 * k;
+                const int as = (it * kC0Sub + j) % kC0AStages;
+                // u8 -> f32 exactly (byte in the mantissa of 2^23, minus 2^23), bf16 = the upper half of that f32
+                uint32_t f[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) f[t] = __float_as_uint(__uint_as_float(0x4B000000u | v[k][t]) - 8388608.0f);
+                uint4 c0, c1;
+                c0.x = __byte_perm(f[0], f[1], 0x7632);
+                c0.y = __byte_perm(f[2], f[3], 0x7632);
+                c0.z = __byte_perm(f[4], f[5], 0x7632);
+                c0.w = __byte_perm(f[6], f[7], 0x7632);
+                c1 = make_uint4(__byte_perm(f[8], zero, 0x7632), 0u, 0u, 0u);
+                ptx::mbar_wait(&a_empty[as], (((it * kC0Sub + j) / kC0AStages) & 1) ^ 1);
+                uint8_t* rowp = sA + as * kC0ABytes + r * 64;
+                *reinterpret_cast<uint4*>(rowp + ((0 ^ xr) << 4)) = c0;
+                *reinterpret_cast<uint4*>(rowp + ((1 ^ xr) << 4)) = c1;
+                *reinterpret_cast<uint4*>(rowp + ((2 ^ xr) << 4)) = c0;
+                *reinterpret_cast<uint4*>(rowp + ((3 ^ xr) << 4)) = c1;
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&a_full[as]);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 2 * kC0Sub * BN);
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host
@@ -1373,6 +1626,7 @@ struct ConvTcPlan {
     int bn, bk;
     int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
     int s2;                    // halo kernel in its stride-2 pixel-pair form
+    bool conv0 = false;        // the first layer on the tensor cores (conv0_tc_kernel)
     int pix_per_image_tiles;   // tiles_x * tiles_y (work items per image and N block)
 };
 
@@ -1706,6 +1960,61 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
 
 void conv_tc_plan_destroy(ConvTcPlan* p) { delete p; }
 
+// First layer on the tensor cores: `wmat` = bf16 [cout = 32][32] rows [hi taps 0..8 | 0 x 7 | lo taps 0..8 | 0 x 7].
+int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* wmat, const float* bias, int act,
+                         const TensorView& dst, int batch, ConvTcPlan** out) {
+    WT_REQUIRE(h % 2 == 0 && w % 16 == 0, "conv0 (tcgen05) needs an even height and a width that is a multiple of 16");
+    WT_REQUIRE(dst.dtype == WT_DT_BF16 && dst.h == h / 2 && dst.w == w / 2 && (dst.ctot * 2) % 16 == 0 &&
+                   (dst.coff * 2) % 16 == 0,
+               "conv0 destination shape");
+    ConvTcPlan* pl = new ConvTcPlan();
+    ConvTcParams& p = pl->prm;
+    memset(&p, 0, sizeof(p));
+    pl->bn = 32; pl->bk = 32; pl->cg = 1; pl->s2 = 0; pl->halo = false;
+    pl->conv0 = true;
+    const int ho = h / 2, wo = w / 2;
+    p.tw = kC0TileW; p.th = kC0TileH; p.tn = 1;
+    p.tiles_x = ceil_div(wo, p.tw); p.tiles_y = ceil_div(ho, p.th); p.tiles_n = batch;
+    p.n_blocks = 1; p.ksize = 3; p.stride = 2; p.cin = 1; p.cin_blocks = 1; p.cout = 32;
+    p.dst_coff = dst.coff;
+    static const int silu_exact = getenv("WT_SILU_EXACT") ? atoi(getenv("WT_SILU_EXACT")) : 0;
+    p.act = (act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : act;
+    p.bias = bias;
+    p.out_w = wo; p.out_h = ho;
+    p.epi_bufs = 2;
+    p.issuers = 1;
+    pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
+    pl->smem_bytes = kC0AStages * kC0ABytes + kEpiGroups * 2 * kStageBufBytes + 2048 + kC0RawStages * kC0RawBytes + 256 +
+                     kBarrierBytes;
+    int rc = 0;
+    {
+        const uint64_t dims[3] = {uint64_t(w), uint64_t(h), uint64_t(batch)};
+        const uint64_t str[2] = {uint64_t(w), uint64_t(w) * h};
+        const uint32_t box[3] = {kC0RawW, kC0RawH, 1};
+        rc |= encode_tmap(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(src), dims, str, box, 0);
+    }
+    {
+        const uint64_t dims[2] = {32, 32};
+        const uint64_t str[1] = {64};
+        const uint32_t box[2] = {32, 32};
+        rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wmat), dims, str, box, 64);
+    }
+    {
+        const uint64_t dims[4] = {uint64_t(dst.ctot), uint64_t(wo), uint64_t(ho), uint64_t(batch)};
+        const uint64_t str[3] = {uint64_t(dst.ctot) * 2, uint64_t(dst.ctot) * 2 * wo, uint64_t(dst.ctot) * 2 * wo * ho};
+        const uint32_t box[4] = {32, uint32_t(p.tw), uint32_t(p.th), 1};
+        rc |= encode_tmap(&p.tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dst.base, dims, str, box, 64);
+    }
+    p.tmR = p.tmD; p.tmP = p.tmD; p.tmB2 = p.tmB; p.tmB2b = p.tmB; p.tmY = p.tmD;
+    for (int i = 0; i < 4; ++i) p.tmA[i] = p.tmD;
+    if (rc) {
+        delete pl;
+        return 1;
+    }
+    *out = pl;
+    return 0;
+}
+
 template <typename Kernel>
 static int launch_kernel(Kernel kernel, bool* configured, const ConvTcParams& prm, int cg, int smem, int grid,
                          cudaStream_t stream) {
@@ -1762,6 +2071,26 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     const int max_ctas = sm_count / cg * cg;
     const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
     const int smem = pl->smem_bytes;
+    if (pl->conv0) {
+        static bool configured = false;
+        if (!configured) {
+            WT_CHECK_CUDA(cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+            configured = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kC0Threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv0_tc_kernel, prm));
+        WT_LAUNCHED();
+        return 0;
+    }
     if (pl->halo) {
         if (pl->s2) {         // 32 -> 32/64 channels, stride 2 (layer 1)
             switch (pl->bn) {

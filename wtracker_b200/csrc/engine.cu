@@ -219,6 +219,18 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             if (e->bufs[o.src].dtype != WT_DT_U8 || e->bufs[o.src].c != 1) return fail("conv0 source must be u8 grey", i);
             if (o.w_off + int64_t(o.cout) * 9 * 4 > weight_bytes || o.b_off + int64_t(o.cout) * 4 > weight_bytes)
                 return fail("weight offsets out of range", i);
+            // chain_w_off of a CONV0 op: the bf16 [32][32] hi | lo weight matrix of the tcgen05 form (-1: CUDA cores)
+            static const int c0tc_env = getenv("WT_CONV0_TC") ? atoi(getenv("WT_CONV0_TC")) : 1;
+            if (o.chain_w_off >= 0 && conv_impl == 0 && c0tc_env && o.cout == 32 && e->bufs[o.src].w % 16 == 0) {
+                if (o.chain_w_off % 16 != 0 || o.chain_w_off + 2048 > weight_bytes) return fail("conv0 weight matrix out of range", i);
+                if (conv0_tc_plan_create(static_cast<const uint8_t*>(e->buf_ptr[o.src]), e->bufs[o.src].h, e->bufs[o.src].w,
+                                         reinterpret_cast<const __nv_bfloat16*>(e->weights + o.chain_w_off),
+                                         reinterpret_cast<const float*>(e->weights + o.b_off), o.act,
+                                         view_of(e, o.dst, o.dst_coff), batch, &e->conv_plan[i])) {
+                    std::string m = wt_last_error();
+                    return fail(m.c_str(), i);
+                }
+            }
         } else if (o.kind != WT_OP_SPPF_POOL && o.kind != WT_OP_UPSAMPLE2X) {
             return fail("unknown op kind", i);
         }
@@ -288,6 +300,10 @@ extern "C" int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op,
                 else rc = conv_simt_launch(e->conv_desc[i], n, stream);
                 break;
             case WT_OP_CONV0:
+                if (e->conv_plan[i]) {
+                    rc = conv_tc_launch(e->conv_plan[i], n, e->sm_count, stream);
+                    break;
+                }
                 rc = conv0_launch(static_cast<const uint8_t*>(e->buf_ptr[o.src]), e->bufs[o.src].h, e->bufs[o.src].w,
                                   reinterpret_cast<const float*>(e->weights + o.w_off),
                                   reinterpret_cast<const float*>(e->weights + o.b_off), o.cout, o.act,

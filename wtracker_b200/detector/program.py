@@ -221,8 +221,18 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     p.blob.extend((w0.sum(1) / 255.0).float().contiguous().numpy().tobytes())      # [cout][3][3]
     b_off = _align(p.blob, 16)
     p.blob.extend(bias0.float().numpy().tobytes())
+    # tcgen05 form of the first layer: per output channel [9 taps hi | 0 x 7 | 9 taps lo | 0 x 7] in bf16, w = hi + lo
+    w9 = (w0.sum(1) / 255.0).float().reshape(c[0], 9)
+    hi = w9.to(torch.bfloat16)
+    lo = (w9 - hi.float()).to(torch.bfloat16)
+    wmat = torch.zeros((c[0], 32), dtype=torch.bfloat16)
+    wmat[:, 0:9] = hi
+    wmat[:, 16:25] = lo
+    wm_off = _align(p.blob, 16)
+    p.blob.extend(wmat.contiguous().view(torch.int16).numpy().tobytes())
     p.ops.append(dict(kind=L.WT_OP_CONV0, name="model.0", src=b_in, src_coff=0, dst=b0, dst_coff=0, res=-1, res_coff=0,
-                      cin=1, cout=c[0], k=3, stride=2, act=L.WT_ACT_SILU, w_off=w_off, b_off=b_off))
+                      cin=1, cout=c[0], k=3, stride=2, act=L.WT_ACT_SILU, w_off=w_off, b_off=b_off,
+                      chain_w_off=wm_off if c[0] == 32 else -1))
     # a stride-2 conv of the backbone feeds only the C2f after it: cv1 is chained onto it where the shapes allow
     c2f(2, (b1, 0), (b2, 0), 4, after=("model.1", (b0, 0)))
     c2f(4, (b3, 0), (b4, 0), 8, after=("model.3", (b2, 0)))                    # x4
