@@ -1,6 +1,7 @@
 """The C-ABI library builds, loads and exports every symbol include/wtracker_b200.h declares
 (no compute calls: there is no GPU on the CPU test box)."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -20,7 +21,12 @@ def test_header_symbols_are_exported(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.wt_abi_version() == 9
+    import re
+
+    from wtracker_b200 import _lib as L
+
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "wtracker_b200.h")).read()
+    assert native_lib.wt_abi_version() == L.ABI_VERSION == int(re.search(r"#define WT_ABI_VERSION (\d+)", header).group(1))
     assert isinstance(native_lib.wt_last_error(), bytes)
     assert native_lib.wt_launch_count() >= 0
 

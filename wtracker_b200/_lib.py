@@ -18,6 +18,8 @@ WT_ACT_NONE, WT_ACT_SILU = 0, 1
 WT_DT_BF16, WT_DT_F32, WT_DT_U8 = 0, 1, 2
 
 
+ABI_VERSION = 9   # WT_ABI_VERSION of include/wtracker_b200.h this binding was written for
+
 class WtLetterbox(C.Structure):
     _fields_ = [
         ("src_w", C.c_int32), ("src_h", C.c_int32),
@@ -133,7 +135,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError here == header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
-        if handle.wt_abi_version() != 9:
+        if handle.wt_abi_version() != ABI_VERSION:
             raise NativeLibraryError("ABI version mismatch between _lib.py and libwtracker_b200.so")
         _lib = handle
     return _lib
