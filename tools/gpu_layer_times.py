@@ -46,7 +46,7 @@ for i, o in enumerate(ops):
     ms = float(per[i])
     h, w, c, _ = eng.program.bufs[o["dst"]]
     flop = 2 * h * w * o["cout"] * o["cin"] * o["k"] ** 2 * batch if o["kind"] in (0, 1) else 0
-    if o.get("chain_w_off", -1) >= 0:
+    if o.get("chain_w_off", -1) >= 0 and o["kind"] == 1:      # (kind 0 = layer 0: its chain_w_off is the tcgen05 weight matrix)
         k2 = o["cat_c"] + o["cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]
         n2 = o["chain_cout"] if o.get("cat_buf", -1) >= 0 else o["cout"]
         flop += 2 * h * w * n2 * k2 * batch
