@@ -90,6 +90,7 @@ struct ConvTcParams {
     int cat_coff;
     // first layer on the tensor cores (conv0_tc_kernel): u8 grey input map [n][in_h][in_w]
     CUtensorMap tmIn;
+    uint32_t mg_nb, mg_tx, mg_ty;   // multipliers for the tile-index divisions by n_blocks, tiles_x, tiles_y (fast_div)
     // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
     // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
     // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
@@ -134,15 +135,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 struct TileCoord {
     int nblk, x0, y0, n0;
 };
+// n / d with the host-computed multiplier floor(2^32 / d) + 1 (exact while n * d < 2^32; 0 = fall back to a division).
+// A runtime integer division is ~35 instructions including XU-pipe conversions and a MUFU.RCP; the small-tile kernels
+// decode a tile every ~1500 clk in each role's loop, where three of them were 10-20 % of the critical path.
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+    if (magic) return int(__umulhi(uint32_t(n), magic));
+    return d == 1 ? n : n / d;
+}
 template <int CG>
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, int rank) {
     TileCoord c;
-    c.nblk = t % p.n_blocks;
-    int m = t / p.n_blocks;
-    int xb = m % p.tiles_x;
-    m /= p.tiles_x;
-    const int yb = m % p.tiles_y;
-    const int nb = m / p.tiles_y;
+    int m = fast_div(t, p.n_blocks, p.mg_nb);
+    c.nblk = t - m * p.n_blocks;
+    int q = fast_div(m, p.tiles_x, p.mg_tx);
+    int xb = m - q * p.tiles_x;
+    const int nb = fast_div(q, p.tiles_y, p.mg_ty);
+    const int yb = q - nb * p.tiles_y;
     if (CG == 2) xb = 2 * xb + rank;
     c.x0 = xb * p.tw;
     c.y0 = yb * p.th;
@@ -2067,6 +2075,16 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items (CTA pairs: per pair)
     prm.n_images = n_images;
     if (prm.num_tiles == 0) return 0;
+    {
+        auto magic = [&](int d) -> uint32_t {
+            if (d <= 1) return 0u;                                           // (d == 1: the plain path, a no-op division)
+            if ((unsigned long long)prm.num_tiles * (unsigned long long)d >= (1ull << 32)) return 0u;
+            return uint32_t((1ull << 32) / (unsigned long long)d) + 1u;
+        };
+        prm.mg_nb = magic(prm.n_blocks);
+        prm.mg_tx = magic(prm.tiles_x);
+        prm.mg_ty = magic(prm.tiles_y);
+    }
     const int cg = pl->cg;
     const int max_ctas = sm_count / cg * cg;
     const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
