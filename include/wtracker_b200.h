@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 9
+#define WT_ABI_VERSION 10
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -237,6 +237,15 @@ int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, i
 int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t* cam_xywh, const int32_t* mic_xywh,
                 const int32_t* plt_xy, int64_t n, int64_t first_frame, int cycle_frame_num, int imaging_frame_num,
                 int frame_h, int frame_w, double* table, int32_t* crop_xywh, uint8_t* crop_legal, void* stream);
+
+/* Derived columns of the analysed log (replaces DataAnalyzer.initialize, wtracker/eval/data_analyzer.py:54-107):
+ *   table : f64 [n][17] rows of bboxes.csv in wt_log_rows' layout (one simulation, consecutive frames)
+ *   out   : f64 [n][30] = frame, cycle, plt_x, plt_y, cam_x, cam_y, cam_w, cam_h, mic_x, mic_y, mic_w, mic_h, wrm_x, wrm_y,
+ *           wrm_w, wrm_h, time, cycle_step, wrm_center_x, wrm_center_y, mic_center_x, mic_center_y, wrm_speed_x,
+ *           wrm_speed_y, wrm_speed, worm_deviation_x, worm_deviation_y, worm_deviation, bbox_error, precise_error (NaN)
+ * speed = centre difference over `period` rows / frame difference (NaN for the first `period` rows); every float column
+ * rounded to 5 decimals exactly as DataFrame.round(5) does (rint(x * 1e5) / 1e5).                                       */
+int wt_analysis_columns(const double* table, int64_t n, int period, int cycle_frame_num, double* out, void* stream);
 
 /* Segmentation-based tracking error (replaces ErrorCalculator.calculate_precise / calculate_segmentation,
  * wtracker/eval/error_calculator.py:19-161): for row i the fraction of the segmented worm — pixels of the

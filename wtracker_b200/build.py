@@ -28,6 +28,7 @@ SOURCES = [
     "metrics.cu",
     "log.cu",
     "precise.cu",
+    "analysis.cu",
     "engine.cu",
 ]
 
