@@ -14,12 +14,15 @@
 // K-major descriptor expects.  Stride-2 convs use four parity views of the input (even/odd rows x
 // even/odd columns), so each tap is again a dense box.
 //
-// Warp roles (352 threads, persistent over tiles): warp 0 = TMA producer, warps 1..2 = MMA issuers
-// (warp 1 also owns the TMEM allocation), warps 3..6 / 7..10 = two epilogue groups (TMEM -> registers
-// -> swizzled smem -> TMA store).  The TMEM accumulator is double-buffered; MMA issuer w and epilogue
-// group w own buffer w, i.e. every second tile of the CTA.  Two issuers because ONE thread cannot issue
-// narrow MMAs fast enough (measured: ~9 uniform-datapath instructions at ~8-10 clk each per UMMA,
-// while a 128x64x16 UMMA occupies the tensor pipe for only 32 clk).
+// Warp roles (608 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; it
+// also owns the TMEM allocation), warp 2 = spare (addend loader, second UMMA chain of the chained forms, optional
+// second issuer), warps 3..10 / 11..18 = two epilogue groups of eight warps (TMEM -> registers -> swizzled smem -> TMA
+// store).  The TMEM accumulator is double-buffered: epilogue group g owns buffer g, i.e. every second tile of the CTA.
+//
+// Kernels in this file: conv_tc_kernel (generic: 1x1, stride-2 3x3, small maps), conv_halo_kernel (3x3 stride 1 with
+// shared-memory halo reuse; stride-2 pixel-pair form for 32 input channels), conv0_tc_kernel (the first layer: im2col
+// rows built by threads).  Fused forms: dot head (wt_op.dot_off), upsampled addend (wt_op.add_buf), chained 1x1 conv
+// (wt_op.chain_w_off), concat chain at a C2f exit (wt_op.cat_buf).
 #include "../../include/wtracker_b200.h"
 #include "conv.cuh"
 #include "ptx.cuh"
