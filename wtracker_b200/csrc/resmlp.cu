@@ -226,7 +226,8 @@ __device__ __forceinline__ void dense_warp(const float* __restrict__ wt, const f
                                            float* out, int nin, int nout, bool relu, int lane) {
     for (int o = lane; o < nout; o += 32) {
         float a = b[o];
-        for (int i = 0; i < nin; ++i) a = fmaf(in[i], wt[i * nout + o], a);
+#pragma unroll 8
+        for (int i = 0; i < nin; ++i) a = fmaf(in[i], wt[i * nout + o], a);   // (same order; the loads run ahead)
         out[o] = relu ? fmaxf(a, 0.f) : a;
     }
     __syncwarp();
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kMlpWarpThreads) resmlp_warp_kernel(const MlpP
         const int n_layers = 2 + p.d.n_blocks * p.d.block_len;
         for (int l = 0; l < n_layers; ++l) {
             const int nout = l == 0 ? H : (l == n_layers - 1 ? p.d.out_dim : p.d.block_dims[(l - 1) % p.d.block_len]);
+#pragma unroll 4
             for (int idx = threadIdx.x; idx < nout * nin; idx += kMlpWarpThreads) {
                 const int o = idx / nin, i = idx - o * nin;
                 sw[off + i * nout + o] = __ldg(p.d.weights + off + idx);
