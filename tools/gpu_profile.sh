@@ -6,7 +6,7 @@
 #   4. ncu --set full with source for the non-conv kernels of a timed step -> simt_<tag>.ncu-rep
 export PYTHONPATH=$PWD
 tag=${1:-rX}
-CONVS_PER_STEP=${2:-53}
+CONVS_PER_STEP=${2:-52}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum,sm__cycles_elapsed.avg
 $CMD > gpurun_out/plain_$tag.log 2>&1 &&

@@ -3,6 +3,8 @@
 #include "../../include/wtracker_b200.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <cudaTypedefs.h>
 
 #include <mutex>
@@ -51,8 +53,14 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* bas
     if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
     else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = fn(out, dtype, cuuint32_t(rank), base, gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // L2 promotion of TMA loads: 128 B by default; WT_TMAP_L2=256 | 64 | 0 for A/B runs
+    static const int l2_env = getenv("WT_TMAP_L2") ? atoi(getenv("WT_TMAP_L2")) : 128;
+    const CUtensorMapL2promotion l2 = l2_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : l2_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : l2_env == 0  ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                                     : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    CUresult r = fn(out, dtype, cuuint32_t(rank), base, gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[512];
         snprintf(buf, sizeof buf,
