@@ -15,8 +15,7 @@
 // even/odd columns), so each tap is again a dense box.
 //
 // Warp roles (608 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; it
-// also owns the TMEM allocation), warp 2 = spare (addend loader, second UMMA chain of the chained forms, optional
-// second issuer), warps 3..10 / 11..18 = two epilogue groups of eight warps (TMEM -> registers -> swizzled smem -> TMA
+// also owns the TMEM allocation), warp 2 = spare (addend loader, second UMMA chain of the chained forms), warps 3..10 / 11..18 = two epilogue groups of eight warps (TMEM -> registers -> swizzled smem -> TMA
 // store).  The TMEM accumulator is double-buffered: epilogue group g owns buffer g, i.e. every second tile of the CTA.
 //
 // Kernels in this file: conv_tc_kernel (generic: 1x1, stride-2 3x3, small maps), conv_halo_kernel (3x3 stride 1 with
@@ -1830,11 +1829,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
             p.stages = 9;   // the ring wraps once per tile: stage index == tap
             const int spare = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
             p.a_stages = spare > kMaxAStages ? kMaxAStages : spare;
-            static const int issuers_env = getenv("WT_CONV_ISSUERS") ? atoi(getenv("WT_CONV_ISSUERS")) : 1;
-            if (issuers_env == 2 && p.a_stages >= 2) {
-                p.a_stages &= ~1;   // slot s is only ever read by issuer s % 2
-                p.issuers = 2;
-            }   // measured slower than one issuer: off by default   // slot s is only ever read by issuer s % 2
+            // (a second MMA issuer warp taking alternate tiles was measured slower and has been retired: the kernels keep
+            // the `issuers` parameter but the plan always sets 1)
         }
         if (p.stages < 2) {
             delete pl;
