@@ -1403,8 +1403,8 @@ __global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_co
     uint8_t* smem = smem_raw;
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;                                            // [kC0AStages][128][64 B]
-    uint8_t* sStage = sA + kC0AStages * kC0ABytes;                 // 2 groups x 32 KB output staging
-    uint8_t* sB = sStage + kEpiGroups * 2 * kStageBufBytes;        // [32][64 B] weights (hi | lo)
+    uint8_t* sStage = sA + kC0AStages * kC0ABytes;                 // 2 groups x 2 x 32 KB output staging (double-buffered)
+    uint8_t* sB = sStage + kEpiGroups * 4 * kStageBufBytes;        // [32][64 B] weights (hi | lo)
     uint8_t* sRaw = sB + 2048;                                     // [kC0RawStages][2816 B]
     float* sBias = reinterpret_cast<float*>(sRaw + kC0RawStages * kC0RawBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 64);
@@ -1508,7 +1508,7 @@ __global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_co
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const bool store_thread = (threadIdx.x - kFirstEpiWarp * 32 - g * kEpiThreads) == 0;
-        uint8_t* stage = sStage + g * 2 * kStageBufBytes;
+        uint8_t* stage0 = sStage + g * 4 * kStageBufBytes;
         const int bar_id = kEpiBarrier + g;
         const int xr = (row >> 1) & 3;
         float bias[16];
@@ -1518,8 +1518,11 @@ __global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_co
         int it = g;
         for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
             const TileCoord tc = decode_tile<1>(p, tile, 0);
+            // two staging tiles per group: the TMA store of the previous super-tile may still be reading the other one
+            // (ncu: with one tile a quarter of the epilogue's samples sat at the barrier behind tma_store_wait_read<0>)
+            uint8_t* stage = stage0 + ((it >> 1) & 1) * 2 * kStageBufBytes;
             ptx::mbar_wait(&tfull_bar[g], (it >> 1) & 1);
-            if (store_thread) ptx::tma_store_wait_read<0>();
+            if (store_thread) ptx::tma_store_wait_read<1>();
             ptx::tc_fence_after();
             ptx::bar_sync(bar_id, kEpiThreads);
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kC0Sub * BN + h * 16;
@@ -1991,7 +1994,7 @@ int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* 
     p.epi_bufs = 2;
     p.issuers = 1;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
-    pl->smem_bytes = kC0AStages * kC0ABytes + kEpiGroups * 2 * kStageBufBytes + 2048 + kC0RawStages * kC0RawBytes + 256 +
+    pl->smem_bytes = kC0AStages * kC0ABytes + kEpiGroups * 4 * kStageBufBytes + 2048 + kC0RawStages * kC0RawBytes + 256 +
                      kBarrierBytes;
     int rc = 0;
     {
