@@ -14,7 +14,7 @@ over a few dozen synthetic worm views) to fire on the worm head and regress its 
 The stride-16/32 levels get zero class weights and a very negative bias (they never fire).
 Everything is deterministic in the seed; uses the fp32 oracle model on the CPU.
 
-    PYTHONPATH=. python tools/calibrate_synthetic.py [seed ...]
+    PYTHONPATH=. python tests/tools/calibrate_synthetic.py [seed ...]
 """
 import json
 import os

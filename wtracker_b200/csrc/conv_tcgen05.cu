@@ -117,7 +117,7 @@ __host__ __device__ constexpr int add_smem_bytes(int bn) { return kEpiGroups * b
 
 // SiLU(v) = v * sigmoid(v) = h * tanh(h) + h with h = v / 2: ONE MUFU op (tanh.approx) per element
 // instead of two (ex2 + rcp) — the epilogue warps are MUFU/issue bound, not the tensor pipe.  Measured on
-// B200 against the fp32 oracle (tools/gpu_detector_check.py): feature and logit errors are identical to
+// B200 against the fp32 oracle (tests/tools/gpu_detector_check.py): feature and logit errors are identical to
 // the ex2+rcp form (both are dominated by the bf16 rounding of the stored activations) and the whole
 // forward is 7 % faster.  WT_SILU_EXACT=1 selects the ex2+rcp form for A/B runs.
 constexpr int kActSiluTanh = 2;

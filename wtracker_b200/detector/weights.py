@@ -26,7 +26,7 @@ def synthetic_state_dict(seed: int = 0, arch: YoloV8Arch | None = None, calibrat
     rounded through fp16 like an ultralytics checkpoint.  Conv weights ~ N(0, 2.2/fan_in) keep the
     activations O(1) through all modules.  With ``calibrated`` the final 1x1 head convolutions are
     replaced by the ones in ``models/synthetic_yolov8s_calib.json`` (made by
-    ``tools/calibrate_synthetic.py``: principal directions of the head features) so that ~1-3 % of
+    ``tests/tools/calibrate_synthetic.py``: principal directions of the head features) so that ~1-3 % of
     the anchors of a synthetic worm frame pass conf 0.1 and the DFL distributions are not flat."""
     arch = arch or YoloV8Arch("s", 1)
     g = torch.Generator().manual_seed(seed)
