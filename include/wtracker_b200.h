@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 10
+#define WT_ABI_VERSION 11
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -185,12 +185,14 @@ int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_pos
  * LoggingController._log_cycle, wtracker/sim/sim_controllers/logging_controller.py:152-155, and the
  * camera / microscope boxes of ViewController.camera_position / micro_position,
  * wtracker/sim/view_controller.py:93-117):
- *   worm_xywh[i] = best box of image i as (x, y, w, h) in FRAME pixels (NaN row when count == 0)
+ *   worm_xywh[i] = best box of image i as (x, y, w, h) in FRAME pixels; when count == 0: a NaN row, or with
+ *                  none_as_zero the row 0, 0, 0, 0 that bboxes.csv holds for such a frame (discretize zeroes the
+ *                  NaN prediction in place before it is logged, logging_controller.py:153-158)
  *   mic_xywh[i]  = microscope box centred like the camera view
  * boxes: f32 [n][max_det][6], count: i32 [n] (outputs of wt_decode_nms); crop_x/y: camera-view origin. */
 int wt_track_rows(const float* boxes, const int32_t* count, int max_det, const int32_t* crop_x, const int32_t* crop_y,
                   int cam_w, int cam_h, int mic_w, int mic_h, double* worm_xywh, double* mic_xywh, int64_t n,
-                  void* stream);
+                  int none_as_zero, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K9  ResMLP position predictor                                                              */
@@ -215,6 +217,46 @@ int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float* y, int64_t
  * table: f64 [table_rows][4]; frame: i32 [n]; offsets: i32 [k] (device); x: f32 [n][4k]; valid: u8 [n]. */
 int wt_mlp_gather(const double* table, int64_t table_rows, const int32_t* frame, const int32_t* offsets, int k,
                   float* x, uint8_t* valid, int64_t n, void* stream);
+
+/* The tail of the hot path as ONE launch (the product path of HotPath / bench.py): for batch items i = 0..n-1, whose
+ * results go to rows first_row + i of the tracking table,
+ *   table[first_row + i], mic_table[first_row + i]  <- wt_track_rows
+ *   x[i], valid[i]                                  <- wt_mlp_gather with frame[i] = first_row + i (rows of this batch
+ *                                                      are taken straight from boxes / count, earlier rows from table)
+ *   y[i]                                            <- wt_resmlp_forward(x[i])      (bit-identical to that entry point)
+ *   err[i]                                          <- wt_bbox_error(table row, mic row)
+ * replaces, per frame: logging_controller.py:152-155 + view_controller.py:93-117, mlp_controllers.py:38-56,
+ * neural/mlp.py:176-188, eval/error_calculator.py:163-195.
+ * weights_t: the ResMLP blob with every layer TRANSPOSED, f32 [in][out] then bias[out], layers in execution order,
+ * padded with zeros to a multiple of 4 floats, 16-byte aligned (mlp.weights is not read).  x may be NULL. */
+#define WT_TAIL_MAX_K 16
+typedef struct wt_tail_args {
+    const float* boxes;            /* f32 [n][max_det][6] (wt_decode_nms)                          */
+    const int32_t* count;          /* i32 [n]                                                       */
+    int32_t max_det;
+    const int32_t* crop_x;         /* i32 [n] camera-view origin in frame px                        */
+    const int32_t* crop_y;
+    int32_t cam_w, cam_h, mic_w, mic_h;
+    double* table;                 /* f64 [table_rows][4] worm xywh by row (read + written)         */
+    double* mic_table;             /* f64 [table_rows][4]                                           */
+    int64_t table_rows, first_row, n;
+    int32_t k;                     /* input boxes per sample (= in_dim / 4)                         */
+    int32_t offsets[WT_TAIL_MAX_K];/* row offsets of the k input boxes (IOConfig.input_frames)      */
+    wt_resmlp_desc mlp;
+    const float* weights_t;
+    float* x;                      /* f32 [n][4k] or NULL                                           */
+    uint8_t* valid;                /* u8 [n]                                                        */
+    float* y;                      /* f32 [n][out_dim]                                              */
+    double* err;                   /* f64 [n]                                                       */
+} wt_tail_args;
+int wt_hot_tail(const wt_tail_args* args, void* stream);
+
+/* Rows of the per-frame result table that the ranks gather at the end of an offline run (the values
+ * YoloController.predict returns, yolo_controller.py:80-90): for detection i of frame first_frame + i
+ *   rows[i] = 8 x 32 bit: f32 x, y, w, h (view px; NaN when nothing passed conf), f32 conf, i32 kept anchor index
+ *             (-1 = none), i32 frame index, i32 valid (0 | 1).   rows: 16-byte aligned. */
+int wt_result_rows(const float* boxes, const int32_t* count, int max_det, int64_t first_frame, int32_t* rows, int64_t n,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* K10  per-step bbox metrics                                                                 */

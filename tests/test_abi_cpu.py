@@ -12,7 +12,7 @@ def test_header_symbols_are_exported(native_lib):
     header = (ROOT / "include" / "wtracker_b200.h").read_text()
     declared = set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", header))
     declared -= {"wt_engine"}
-    assert len(declared) == 23
+    assert len(declared) == 25
     from wtracker_b200 import _lib
 
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
@@ -35,7 +35,8 @@ def test_struct_sizes_match_header(native_lib):
     from wtracker_b200 import _lib as L
 
     # sizes printed by a C program compiled against include/wtracker_b200.h (x86-64 SysV)
-    expect = {"WtLetterbox": 64, "WtBuf": 16, "WtOp": 120, "WtPostParams": 40, "WtHeadLevel": 96, "WtResmlpDesc": 72}
+    expect = {"WtLetterbox": 64, "WtBuf": 16, "WtOp": 120, "WtPostParams": 40, "WtHeadLevel": 96, "WtResmlpDesc": 72,
+              "WtTailArgs": 280}
     for name, size in expect.items():
         assert ctypes.sizeof(getattr(L, name)) == size, name
 
@@ -48,14 +49,15 @@ def test_struct_sizes_against_compiled_header(tmp_path):
         return
     src = tmp_path / "sz.c"
     src.write_text(f'#include "{ROOT}/include/wtracker_b200.h"\n#include <stdio.h>\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(wt_letterbox), sizeof(wt_buf), sizeof(wt_op),'
-                   'sizeof(wt_post_params), sizeof(wt_head_level), sizeof(wt_resmlp_desc)); return 0;}\n')
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu", sizeof(wt_letterbox), sizeof(wt_buf), sizeof(wt_op),'
+                   'sizeof(wt_post_params), sizeof(wt_head_level), sizeof(wt_resmlp_desc), sizeof(wt_tail_args)); return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     from wtracker_b200 import _lib as L
 
-    got = [ctypes.sizeof(c) for c in (L.WtLetterbox, L.WtBuf, L.WtOp, L.WtPostParams, L.WtHeadLevel, L.WtResmlpDesc)]
+    got = [ctypes.sizeof(c) for c in (L.WtLetterbox, L.WtBuf, L.WtOp, L.WtPostParams, L.WtHeadLevel, L.WtResmlpDesc,
+                                      L.WtTailArgs)]
     assert sizes == got
 
 

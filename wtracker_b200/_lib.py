@@ -18,7 +18,7 @@ WT_ACT_NONE, WT_ACT_SILU = 0, 1
 WT_DT_BF16, WT_DT_F32, WT_DT_U8 = 0, 1, 2
 
 
-ABI_VERSION = 10  # WT_ABI_VERSION of include/wtracker_b200.h this binding was written for
+ABI_VERSION = 11  # WT_ABI_VERSION of include/wtracker_b200.h this binding was written for
 
 class WtLetterbox(C.Structure):
     _fields_ = [
@@ -81,6 +81,22 @@ class WtResmlpDesc(C.Structure):
     ]
 
 
+WT_TAIL_MAX_K = 16
+
+
+class WtTailArgs(C.Structure):
+    _fields_ = [
+        ("boxes", C.c_void_p), ("count", C.c_void_p), ("max_det", C.c_int32),
+        ("crop_x", C.c_void_p), ("crop_y", C.c_void_p),
+        ("cam_w", C.c_int32), ("cam_h", C.c_int32), ("mic_w", C.c_int32), ("mic_h", C.c_int32),
+        ("table", C.c_void_p), ("mic_table", C.c_void_p),
+        ("table_rows", C.c_int64), ("first_row", C.c_int64), ("n", C.c_int64),
+        ("k", C.c_int32), ("offsets", C.c_int32 * WT_TAIL_MAX_K),
+        ("mlp", WtResmlpDesc),
+        ("weights_t", C.c_void_p), ("x", C.c_void_p), ("valid", C.c_void_p), ("y", C.c_void_p), ("err", C.c_void_p),
+    ]
+
+
 # every symbol include/wtracker_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "wt_last_error": (C.c_char_p, []),
@@ -99,10 +115,12 @@ SIGNATURES = {
     "wt_decode_nms": (C.c_int, [C.POINTER(WtHeadLevel), C.c_int, C.c_int, C.POINTER(WtPostParams), C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "wt_track_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "wt_resmlp_forward": (C.c_int, [C.POINTER(WtResmlpDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mlp_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_void_p]),
+    "wt_hot_tail": (C.c_int, [C.POINTER(WtTailArgs), C.c_void_p]),
+    "wt_result_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_bbox_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mse_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_analysis_columns": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -25,6 +25,7 @@ SOURCES = [
     "pre.cu",
     "post.cu",
     "resmlp.cu",
+    "tail.cu",
     "metrics.cu",
     "log.cu",
     "precise.cu",

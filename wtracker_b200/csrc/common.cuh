@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 namespace wt {
@@ -41,6 +42,28 @@ extern std::atomic<uint64_t> g_launch_count;        // kernels launched by this 
     } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Opt-in for > 48 KB of dynamic shared memory.  Function attributes belong to the (device, context) pair, so the
+// "already raised to N bytes" state is kept PER DEVICE (one engine per GPU in one process is legal: DetectorEngine,
+// ResMLPEngine and HotPath all take a `device`), behind a mutex (launch paths are re-entrant per engine + stream).
+struct SmemOptIn {
+    static constexpr int kMaxDevices = 64;
+    std::mutex m;
+    size_t bytes[kMaxDevices] = {};
+};
+template <typename Kernel>
+inline cudaError_t opt_in_smem(Kernel kernel, SmemOptIn& st, size_t want) {
+    if (want <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= SmemOptIn::kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(want));
+    std::lock_guard<std::mutex> lock(st.m);
+    if (want <= st.bytes[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(want));
+    if (e == cudaSuccess) st.bytes[dev] = want;
+    return e;
+}
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may start (up to its
 // griddepcontrol.wait) while the previous kernel of the stream drains.  The kernel MUST execute

@@ -2026,12 +2026,9 @@ int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* 
 }
 
 template <typename Kernel>
-static int launch_kernel(Kernel kernel, bool* configured, const ConvTcParams& prm, int cg, int smem, int grid,
+static int launch_kernel(Kernel kernel, SmemOptIn* opt_in, const ConvTcParams& prm, int cg, int smem, int grid,
                          cudaStream_t stream) {
-    if (!*configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        *configured = true;
-    }
+    WT_CHECK_CUDA(opt_in_smem(kernel, *opt_in, kSmemBudget));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -2061,14 +2058,14 @@ static int launch_kernel(Kernel kernel, bool* configured, const ConvTcParams& pr
 
 template <int BN, int BK, int CG>
 static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
-    static bool configured = false;
-    return launch_kernel(conv_tc_kernel<BN, BK, CG>, &configured, prm, CG, smem, grid, stream);
+    static SmemOptIn opt_in;
+    return launch_kernel(conv_tc_kernel<BN, BK, CG>, &opt_in, prm, CG, smem, grid, stream);
 }
 
 template <int BN, int BK, int CG, int S2 = 0>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
-    static bool configured = false;
-    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2>, &configured, prm, CG, smem, grid, stream);
+    static SmemOptIn opt_in;
+    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2>, &opt_in, prm, CG, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
@@ -2092,11 +2089,8 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
     const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
     const int smem = pl->smem_bytes;
     if (pl->conv0) {
-        static bool configured = false;
-        if (!configured) {
-            WT_CHECK_CUDA(cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-            configured = true;
-        }
+        static SmemOptIn opt_in;
+        WT_CHECK_CUDA(opt_in_smem(conv0_tc_kernel, opt_in, kSmemBudget));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kC0Threads);

@@ -567,12 +567,8 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
     WT_REQUIRE(smem <= 200 * 1024, "SPPF feature map too large for the shared-memory pool kernel");
     if (n_images == 0) return 0;
     auto* kernel = !small ? sppf_pool_generic_kernel : (G == 4 ? sppf_pool_kernel<4> : sppf_pool_kernel<1>);
-    static size_t configured[3] = {0, 0, 0};
-    const int slot = !small ? 2 : (G == 4);
-    if (smem > 48 * 1024 && smem > configured[slot]) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured[slot] = smem;
-    }
+    static SmemOptIn opt_in[3];
+    WT_CHECK_CUDA(opt_in_smem(kernel, opt_in[!small ? 2 : (G == 4)], smem));
     dim3 grid(c / (kPoolCg * G), n_images);
     WT_CHECK_CUDA(launch_pdl(kernel, grid, dim3(kPoolThreads * G), smem, stream,
                              static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,

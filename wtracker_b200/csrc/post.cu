@@ -350,12 +350,13 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
 __global__ void track_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ count, int max_det,
                                   const int32_t* __restrict__ crop_x, const int32_t* __restrict__ crop_y, int cam_w,
                                   int cam_h, int mic_w, int mic_h, double* __restrict__ worm, double* __restrict__ mic,
-                                  long long n) {
+                                  long long n, int none_as_zero) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double cx = double(crop_x[i]), cy = double(crop_y[i]);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     double w0 = nan, w1 = nan, w2 = nan, w3 = nan;
+    if (none_as_zero) w0 = w1 = w2 = w3 = 0.0;   // what bboxes.csv holds for such a frame (logging_controller.py:153-158)
     if (count[i] > 0) {
         const float* b = boxes + i * max_det * 6;
         // xyxy -> xywh in float32 (BoxConverter.to_xywh on the fp32 result), then shifted by the
@@ -378,12 +379,12 @@ __global__ void track_rows_kernel(const float* __restrict__ boxes, const int32_t
 
 extern "C" int wt_track_rows(const float* boxes, const int32_t* count, int max_det, const int32_t* crop_x,
                              const int32_t* crop_y, int cam_w, int cam_h, int mic_w, int mic_h, double* worm_xywh,
-                             double* mic_xywh, int64_t n, void* stream) {
+                             double* mic_xywh, int64_t n, int none_as_zero, void* stream) {
     using namespace wt;
     if (n == 0) return 0;
     WT_REQUIRE(boxes && count && crop_x && crop_y && worm_xywh && mic_xywh, "null argument");
     track_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        boxes, count, max_det, crop_x, crop_y, cam_w, cam_h, mic_w, mic_h, worm_xywh, mic_xywh, n);
+        boxes, count, max_det, crop_x, crop_y, cam_w, cam_h, mic_w, mic_h, worm_xywh, mic_xywh, n, none_as_zero);
     WT_LAUNCHED();
     return 0;
 }
@@ -431,11 +432,8 @@ extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, c
     p.sc_idx = reinterpret_cast<int32_t*>(sc + size_t(n) * total * 20);
     p.sc_logit = reinterpret_cast<float*>(sc + size_t(n) * total * 24);
     if (n == 0) return 0;
-    static size_t configured = 0;
-    if (smem > configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static SmemOptIn opt_in;
+    WT_CHECK_CUDA(opt_in_smem(post_kernel, opt_in, smem));
     bool any_feat = false;
     for (int l = 0; l < n_levels; ++l) any_feat |= levels[l].cls_feat != nullptr;
     if (any_feat) {

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) pre_kernel(const PreParams p) {
     const int Y = gid / groups_per_row;
     const int X0 = (gid - Y * groups_per_row) << 4;
 
-    const int f = p.frame_idx[img];
+    const int f = clampi(p.frame_idx[img], 0, p.n_frames - 1);   // a stale index must not read outside `frames`
     const uint8_t* frame = p.frames + size_t(f) * p.fh * p.fw;
     const int cx = p.crop_x[img], cy = p.crop_y[img];
     const int ry = Y - p.lb.pad_top;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) pre_crop_kernel(const PreParams p) {
     if (gid >= groups_per_row * (p.lb.dst_h / kCropRows)) return;
     const int Yq = gid / groups_per_row;
     const int X0 = (gid - Yq * groups_per_row) << 4;
-    const uint8_t* frame = p.frames + size_t(p.frame_idx[img]) * p.fh * p.fw;
+    const uint8_t* frame = p.frames + size_t(clampi(p.frame_idx[img], 0, p.n_frames - 1)) * p.fh * p.fw;
     const int cx = p.crop_x[img], cy = p.crop_y[img];
     const bool x_in = cx + X0 >= 0 && cx + X0 + 32 <= p.fw;   // one group of slack for the second vector load
     uint4 v[kCropRows];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kResizeThreads) pre_resize_kernel(const PrePar
     const int img = blockIdx.y, Y0 = blockIdx.x * kResizeRows;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rows_here = min(kResizeRows, lb.dst_h - Y0);
-    const uint8_t* frame = p.frames + size_t(p.frame_idx[img]) * p.fh * p.fw;
+    const uint8_t* frame = p.frames + size_t(clampi(p.frame_idx[img], 0, p.n_frames - 1)) * p.fh * p.fw;
     const int cx = p.crop_x[img], cy = p.crop_y[img];
 
     // view rows this tile reads: [vbase, vtop]
@@ -266,6 +266,10 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
     if (n == 0) return 0;
     WT_REQUIRE(frames && frame_idx && crop_x && crop_y && lb, "null argument");
     WT_REQUIRE(out_u8 || out_f32, "no output requested");
+    WT_REQUIRE(n_frames >= 1 && frame_h >= 1 && frame_w >= 1, "empty frame buffer");
+    // the 128-bit load paths align on absolute addresses and may touch up to 15 bytes in front of a row: legal inside
+    // an allocation whose base is 16-byte aligned (every cudaMalloc / torch tensor start), not for an odd sub-view
+    WT_REQUIRE(reinterpret_cast<uintptr_t>(frames) % 16 == 0, "frames must be 16-byte aligned");
     WT_REQUIRE(lb->new_w + lb->pad_left <= lb->dst_w && lb->new_h + lb->pad_top <= lb->dst_h, "letterbox geometry");
     const bool resize = !(lb->new_w == lb->src_w && lb->new_h == lb->src_h);
     if (resize) WT_REQUIRE(lb->xofs && lb->xcoef && lb->yofs && lb->ycoef, "resize tables missing");
@@ -296,11 +300,8 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
         const int pitch = (lb->src_w + 15) & ~15;
         const int smem = max_rows * pitch;
         if (smem <= 200 * 1024) {
-            static int configured = 0;
-            if (smem > configured) {
-                WT_CHECK_CUDA(cudaFuncSetAttribute(pre_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                configured = 200 * 1024;
-            }
+            static SmemOptIn opt_in;
+            WT_CHECK_CUDA(opt_in_smem(pre_resize_kernel, opt_in, 200 * 1024));
             dim3 rgrid((lb->dst_h + kResizeRows - 1) / kResizeRows, n);
             pre_resize_kernel<<<rgrid, kResizeThreads, smem, static_cast<cudaStream_t>(stream)>>>(p, pitch);
             WT_LAUNCHED();

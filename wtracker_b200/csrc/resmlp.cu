@@ -355,11 +355,8 @@ extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float*
     if (n <= 2048) {   // latency-bound regime: one warp per sample
         const size_t wsmem = (size_t((d->n_weights + 31) & ~31) + size_t(kMlpWarpThreads / 32) * 3 * maxw) * sizeof(float);
         WT_REQUIRE(wsmem <= 220 * 1024, "ResMLP too large for the shared-memory kernel");
-        static size_t wconfigured = 0;
-        if (wsmem > 48 * 1024 && wsmem > wconfigured) {
-            WT_CHECK_CUDA(cudaFuncSetAttribute(resmlp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsmem)));
-            wconfigured = wsmem;
-        }
+        static SmemOptIn wopt;
+        WT_CHECK_CUDA(opt_in_smem(resmlp_warp_kernel, wopt, wsmem));
         const long long wblocks = (n + kMlpWarpThreads / 32 - 1) / (kMlpWarpThreads / 32);
         resmlp_warp_kernel<<<(unsigned)wblocks, kMlpWarpThreads, wsmem, static_cast<cudaStream_t>(stream)>>>(p);
         WT_LAUNCHED();
@@ -383,11 +380,8 @@ extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float*
         wp = (wp + 3) & ~3LL;
         const size_t psmem = size_t(wp) * 4 + size_t(d->hidden + tw0 + tw1) * kPairLd * 8;
         if (psmem <= 220 * 1024) {
-            static size_t pconfigured = 0;
-            if (psmem > 48 * 1024 && psmem > pconfigured) {
-                WT_CHECK_CUDA(cudaFuncSetAttribute(resmlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
-                pconfigured = psmem;
-            }
+            static SmemOptIn popt;
+            WT_CHECK_CUDA(opt_in_smem(resmlp_pair_kernel, popt, psmem));
             long long pblocks = (n + 2 * kPairThreads - 1) / (2 * kPairThreads);
             int sm_count = 148;
             wt_device_info(&sm_count, nullptr, nullptr);
@@ -400,11 +394,8 @@ extern "C" int wt_resmlp_forward(const wt_resmlp_desc* d, const float* x, float*
     }
     const size_t smem = (size_t((d->n_weights + 31) & ~31) + size_t(3) * maxw * kLd) * sizeof(float);
     WT_REQUIRE(smem <= 220 * 1024, "ResMLP too large for the shared-memory kernel");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        WT_CHECK_CUDA(cudaFuncSetAttribute(resmlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
+    static SmemOptIn opt;
+    WT_CHECK_CUDA(opt_in_smem(resmlp_kernel, opt, smem));
     const long long blocks = (n + kMlpThreads - 1) / kMlpThreads;
     resmlp_kernel<<<(unsigned)blocks, kMlpThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     WT_LAUNCHED();

@@ -61,6 +61,21 @@ def pack_resmlp(model: WormPredictor) -> tuple[np.ndarray, dict]:
     return blob, desc
 
 
+def transpose_blob(blob: np.ndarray, d: dict) -> np.ndarray:
+    """The same layers with every weight matrix stored [in][out] (then bias[out]), zero-padded to a multiple of 4
+    floats: the layout ``wt_hot_tail`` stages with plain 16-byte copies (wt_tail_args.weights_t)."""
+    dims = [d["hidden"]] + list(d["block_dims"]) * d["n_blocks"] + [d["out_dim"]]
+    out, off, nin = [], 0, d["in_dim"]
+    for nout in dims:
+        w = blob[off: off + nout * nin].reshape(nout, nin)
+        out += [np.ascontiguousarray(w.T).reshape(-1), blob[off + nout * nin: off + nout * nin + nout]]
+        off += nout * nin + nout
+        nin = nout
+    assert off == blob.size
+    t = np.concatenate(out).astype(np.float32)
+    return np.concatenate([t, np.zeros((-t.size) % 4, np.float32)])
+
+
 class ResMLPEngine:
     def __init__(self, model: WormPredictor, device: str = "cuda:0"):
         if not torch.cuda.is_available():
@@ -71,9 +86,11 @@ class ResMLPEngine:
         blob, d = pack_resmlp(model)
         self.shape = d
         self.weights = torch.from_numpy(blob).to(self.device)
+        self.weights_t = torch.from_numpy(transpose_blob(blob, d)).to(self.device)
         dims = (C.c_int32 * 8)(*(d["block_dims"] + [0] * (8 - len(d["block_dims"]))))
         self._desc = L.WtResmlpDesc(d["in_dim"], d["hidden"], d["out_dim"], d["n_blocks"], d["block_len"], dims,
                                     self.weights.data_ptr(), int(self.weights.numel()))
+        self.desc = self._desc
         self._host_in = torch.empty((1, d["in_dim"]), dtype=torch.float32).pin_memory()
         self._host_out = torch.empty((1, d["out_dim"]), dtype=torch.float32).pin_memory()
         self._dev_in = torch.empty((1, d["in_dim"]), dtype=torch.float32, device=self.device)

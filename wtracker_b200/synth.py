@@ -112,3 +112,58 @@ def camera_view(frame: np.ndarray, pos_xy: tuple[int, int], size: int) -> np.nda
     ys = np.clip(np.arange(y0, y0 + size), 0, h - 1)
     xs = np.clip(np.arange(x0, x0 + size), 0, w - 1)
     return frame[np.ix_(ys, xs)]
+
+
+def render_frames_device(track: np.ndarray, seed: int, device, frame_hw: tuple[int, int] = (FRAME_H, FRAME_W),
+                         first: int = 0, count: int | None = None):
+    """``render_frame`` for frames [first, first + count) of ``track`` written straight into a u8 [count, h, w]
+    tensor on ``device`` (the sweep / offline workloads hold hundreds of frames in HBM; rendering them with numpy
+    and uploading costs ~30 ms each).  Same integer hash and the same float64 operations one by one (separate
+    elementwise kernels: no FMA contraction), so the pixels equal ``render_frame``'s (tests/test_gpu_batched.py).
+    Data generation only — not part of the hot path."""
+    import torch
+
+    h, w = frame_hw
+    count = track.shape[0] - first if count is None else count
+    dev = torch.device(device)
+    M = 0xFFFFFFFF
+    yy = torch.arange(h, dtype=torch.int64, device=dev)[:, None]
+    xx = torch.arange(w, dtype=torch.int64, device=dev)[None, :]
+    base = ((xx * 0x27D4EB2F) & M) ^ ((yy * 0x165667B1) & M)
+
+    def hash_u32(x):
+        x = x ^ (x >> 16)
+        x = (x * 0x7FEB352D) & M
+        x = x ^ (x >> 15)
+        x = (x * 0x846CA68B) & M      # (the int64 product wraps, its low 32 bits are the uint32 product)
+        return x ^ (x >> 16)
+
+    out = torch.empty((count, h, w), dtype=torch.uint8, device=dev)
+    for j in range(count):
+        fi = first + j
+        key = (int(seed) * 0x9E3779B1 ^ int(fi) * 0x85EBCA77) & M
+        noise = hash_u32(base ^ key) % 13
+        img = (194 + noise).to(torch.uint8)
+        cx, cy, ang = (float(v) for v in track[fi])
+        x0, x1 = int(max(0, cx - 110)), int(min(w, cx + 110))
+        y0, y1 = int(max(0, cy - 110)), int(min(h, cy + 110))
+        if x1 > x0 and y1 > y0:
+            ys = torch.arange(y0, y1, dtype=torch.float64, device=dev)[:, None]
+            xs = torch.arange(x0, x1, dtype=torch.float64, device=dev)[None, :]
+            dx, dy = xs - cx, ys - cy
+            ca, sa = float(np.cos(ang)), float(np.sin(ang))
+            u = dx * ca + dy * sa
+            v = -dx * sa + dy * ca
+            uc = torch.clamp(u, -80.0, 0.0)
+            taper = 1.0 + 0.75 * uc / 80.0
+            du = u - uc
+            body = du * du + v * v <= (4.0 * taper) * (4.0 * taper)
+            head = dx * dx + dy * dy <= 7.0 ** 2
+            sub = img[y0:y1, x0:x1]
+            nz = (noise[y0:y1, x0:x1] % 5).to(torch.uint8)
+            shade = (68.0 - 70.0 * uc / 80.0).to(torch.uint8) + nz
+            sub = torch.where(body, shade, sub)
+            sub = torch.where(head, 22 + nz, sub)
+            img[y0:y1, x0:x1] = sub
+        out[j] = img
+    return out
