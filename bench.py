@@ -90,17 +90,11 @@ def sim_setup(geometry: str, n_frames: int, frames: np.ndarray, track: np.ndarra
 
     class PoolReader(ArrayReader):
         def __init__(self, pool, n):
-            self._n = n
             super().__init__(pool)
             self._files = [str(i) for i in range(n)]
 
-        def __len__(self):
-            return self._n
-
         def __getitem__(self, idx):
-            if idx < 0 or idx >= self._n:
-                raise IndexError("index out of bounds")
-            return self._frames[idx % self._frames.shape[0]]
+            return self._frames[self._check(idx) % self._frames.shape[0]]
 
     ppm, imgsz = (90, 384) if geometry == "R" else (160, 640)
     init = (int(track[0, 0]), int(track[0, 1]))

@@ -132,3 +132,36 @@ def test_bbox_utils(golden):
     assert np.allclose(BoxConverter.to_xywh(xyxy, BoxFormat.XYXY), clean)
     assert np.allclose(BoxConverter.to_yolo(clean, BoxFormat.XYWH)[:, :2], golden["center_out"])
     assert BoxUtils.center(np.array([1.0, 2.0, 4.0, 6.0])).tolist() == [3.0, 5.0]
+
+
+def test_file_reader_listing_stream_and_batches(tmp_path):
+    """FrameReader over image files (reference: utils/frame_reader.py:9-157) + the batched access the ingest path uses."""
+    import cv2
+
+    from wtracker_b200.utils.frame_reader import FrameReader, FrameStream
+
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 255, (24, 32), dtype=np.uint8) for _ in range(5)]
+    for i, im in enumerate(imgs):
+        cv2.imwrite(str(tmp_path / f"frame_{i:04d}.png"), im)
+    (tmp_path / "notes").write_text("x")
+    (tmp_path / "other.txt").write_text("x")
+    (tmp_path / "sub.dir").mkdir()
+    r = FrameReader.create_from_template(str(tmp_path), "frame_{:04d}.png")
+    assert r.files == [f"frame_{i:04d}.png" for i in range(5)] and len(r) == 5
+    assert r.frame_shape == (24, 32) and r.frame_size == (24, 32) and r.read_format == 0
+    assert FrameReader.create_from_directory(str(tmp_path)).files == r.files + ["other.txt"]
+    assert all(np.array_equal(r[i], imgs[i]) for i in range(5))
+    with pytest.raises(IndexError):
+        r[5]
+    s = r.make_stream()
+    assert isinstance(s, FrameStream) and s.index == -1 and not s.can_read()
+    assert [int(f.sum()) for f in s] == [int(im.sum()) for im in imgs]
+    assert s.seek(2) and np.array_equal(s.read(), imgs[2]) and s.read() is s.read()
+    s.reset()
+    assert s.index == -1
+    assert np.array_equal(r.read_batch([4, 0, 2]), np.stack([imgs[4], imgs[0], imgs[2]]))
+    a = ArrayReader(np.stack(imgs))
+    assert np.array_equal(a.read_batch(range(1, 4)), np.stack(imgs[1:4])) and a.frame_shape == (24, 32)
+    d = DummyReader(3, (10, 12), colored=False)
+    assert len(d) == 3 and d.frame_shape == (10, 12) and (d[1] == 255).all()

@@ -43,6 +43,13 @@ CASES = [
     (40, 160, 160, 32, 32, 3, 1, 1, 1, 0),   # BN 32 resident, ~110 tiles per CTA
     (64, 40, 40, 256, 128, 3, 1, 1, 0, 0),   # 4 halo blocks per tile, streamed weights
     (64, 20, 20, 512, 512, 1, 1, 1, 0, 0),   # many K blocks per tile through a short ring
+    # tile groups (NT pixel tiles per weight pass): odd batches leave a phantom tile in the last group
+    (3, 40, 40, 128, 128, 3, 1, 1, 0, 0),
+    (5, 80, 80, 64, 64, 3, 1, 1, 1, 0),      # resident weights + residual
+    (7, 160, 160, 32, 32, 3, 1, 1, 1, 0),    # BN 32 / BK 32 (groups of four)
+    (9, 40, 40, 256, 64, 3, 1, 1, 0, 0),
+    (33, 80, 80, 128, 128, 3, 1, 1, 1, 0),   # ~11 groups per CTA, streamed weights, residual
+    (6, 80, 80, 128, 192, 3, 1, 1, 0, 0),    # BN 192: one tile per pass
 ]
 
 # chained conv + 1x1 (wt_selftest_conv_chain): batch, h, w, cin, cout, k, stride

@@ -53,7 +53,7 @@ struct SmemOptIn {
 };
 template <typename Kernel>
 inline cudaError_t opt_in_smem(Kernel kernel, SmemOptIn& st, size_t want) {
-    if (want <= 48 * 1024) return cudaSuccess;
+    // (no "dynamic <= 48 KB needs nothing" shortcut: the limit applies to static + dynamic shared memory together)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

@@ -97,6 +97,11 @@ struct ConvTcParams {
     // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
     // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
     int issuers;
+    // halo kernel: pixel tiles per weight pass (NT template parameter).  A work item is a GROUP of nt tiles at the same
+    // patch position of nt consecutive images; every weight tile streamed from L2 feeds the MMAs of all of them (the
+    // 3x3 layers are bound by the L2 -> shared-memory fill, ~86 % of it weights: DESIGN.md), nt accumulators sit side
+    // by side in TMEM and an epilogue group drains all of them.
+    int nt;
 };
 
 template <int BN, int BK>
@@ -156,7 +161,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
     if (CG == 2) xb = 2 * xb + rank;
     c.x0 = xb * p.tw;
     c.y0 = yb * p.th;
-    c.n0 = nb * p.tn;
+    c.n0 = nb * p.tn * p.nt;
     return c;
 }
 
@@ -171,7 +176,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
 
 // Fused class-logit head (wt_op.dot_off): thread (row, h) sums its half of the pixel's channels, the halves meet
 // in shared memory.
-template <int BN, int CG>
+template <int BN, int CG, int NT>
 __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                                   uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                                   int warp, int lane, int rank) {
@@ -190,7 +195,9 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
         const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + h * (BN / 2);
+#pragma unroll 1
+        for (int sub = 0; sub < NT; ++sub) {
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * NT + sub) * BN + h * (BN / 2);
         const float* bias = sBias + h * (BN / 2);
         const float* dwh = dw + h * (BN / 2);
         float dot = 0.f;
@@ -199,7 +206,7 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
             uint32_t acc[16];
             ptx::tmem_ld_32x16(t_row + c * 16, acc);
             ptx::tmem_ld_wait();
-            if (c == BN / 32 - 1) {
+            if (c == BN / 32 - 1 && sub == NT - 1) {
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -226,22 +233,23 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
                 }
             }
         }
-        float* slot = part + aphase * kTileM;
+        float* slot = part + (aphase * NT + sub) * kTileM;
         if (h == 1) slot[row] = dot;
-        ptx::bar_sync(bar_id, kEpiThreads);   // (the slot is rewritten two tiles of this group later: one more barrier in between)
+        ptx::bar_sync(bar_id, kEpiThreads);   // (the slot is rewritten two work items of this group later: one more barrier in between)
         if (h == 0) {
             const int px = tc.x0 + row % p.tw;
             const int py = tc.y0 + (row / p.tw) % p.th;
-            const int pn = tc.n0 + row / (p.tw * p.th);
+            const int pn = tc.n0 + sub + row / (p.tw * p.th);
             if (px < p.out_w && py < p.out_h && pn < p.n_images)
                 p.dot_out[(size_t(pn) * p.out_h + py) * p.out_w + px] = (dot + slot[row]) + dw[p.cout];
+        }
         }
     }
 }
 
 // CW = accumulator columns per thread and staging unit: 32 (bf16 output, units of 64 channels = 128-byte staging
 // rows) or 16 (f32 output: units of 32 channels = 128-byte rows; bf16 with BN == 32: one unit of 64-byte rows).
-template <int BN, int CG, int CW>
+template <int BN, int CG, int CW, int NT>
 __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                                  uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
                                                  uint32_t tmem_base, int warp, int lane, int rank,
@@ -286,10 +294,13 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
 
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + h * CW;
 
 #pragma unroll 1
-        for (int unit = 0; unit < kUnits; ++unit) {
+        for (int su = 0; su < NT * kUnits; ++su) {
+            const int sub = NT == 1 ? 0 : su / kUnits;          // pixel tile of the group (image n0 + sub)
+            const int unit = NT == 1 ? su : su - sub * kUnits;
+            const int n0s = n0 + sub;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * NT + sub) * BN + h * CW;
             const int sb = two_bufs ? (unit_counter & 1) : 0;
             uint8_t* stage_buf = sStage + sb * kStageBufBytes;
             uint32_t acc[CW];
@@ -302,10 +313,10 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             ptx::bar_sync(bar_id, kEpiThreads);
             if (p.has_res && store_thread) {
                 ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
-                ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, y0, n0);
+                ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, y0, n0s);
             }
             ptx::tmem_ld_wait();
-            if (unit == kUnits - 1) {
+            if (su == NT * kUnits - 1) {
                 // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -372,7 +383,7 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
                     for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
                 }
             }
-            if (p.has_add && unit == kUnits - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
+            if (p.has_add && su == NT * kUnits - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&add_empty[g]);
             }
@@ -423,7 +434,7 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             ptx::fence_proxy_async_smem();
             ptx::bar_sync(bar_id, kEpiThreads);
             if (store_thread) {
-                ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * kUnitCh, x0, y0, n0);
+                ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * kUnitCh, x0, y0, n0s);
                 ptx::tma_store_commit();
             }
             ++unit_counter;
@@ -750,30 +761,30 @@ __device__ __forceinline__ void conv_cat_issuer(const ConvTcParams& p, const uin
     }
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int NT = 1>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
                                               uint32_t tmem_base, int warp, int lane, int rank,
                                               const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
                                               uint64_t* add_empty = nullptr, uint64_t* chain_bars = nullptr) {
     if (p.chain) {
-        if constexpr ((BN == 64 || BN == 128) && CG == 1)
+        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1)
             conv_epilogue_chain<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, chain_bars, tmem_base, warp, lane, rank);
         return;
     }
     if (p.dot_w) {
-        conv_epilogue_dot<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane, rank);
+        conv_epilogue_dot<BN, CG, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane, rank);
         return;
     }
     if constexpr (BN >= 64) {
         if (!p.out_f32) {
-            conv_epilogue_cw<BN, CG, 32>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane,
-                                         rank, sAddAll, add_full, add_empty);
+            conv_epilogue_cw<BN, CG, 32, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane,
+                                             rank, sAddAll, add_full, add_empty);
             return;
         }
     }
-    conv_epilogue_cw<BN, CG, 16>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane, rank,
-                                 sAddAll, add_full, add_empty);
+    conv_epilogue_cw<BN, CG, 16, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane, rank,
+                                     sAddAll, add_full, add_empty);
 }
 
 template <int BN, int BK, int CG>
@@ -1062,25 +1073,28 @@ struct HaloSmem {
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN, int BK, int CG, int S2>
+template <int BN, int BK, int CG, int S2, int NT>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
     static_assert(!S2 || (BK == 32 && CG == 1), "the stride-2 pair form is written for 32 input channels");
+    static_assert(NT == 1 || (CG == 1 && 2 * NT * BN <= 512), "tile groups: single-CTA MMAs, 2 x NT accumulators in TMEM");
     using L = HaloSmem<BN, BK, CG, S2>;
     constexpr int kARowBytes = L::kARowBytes;
     const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
     const int first = blockIdx.x / CG, step = gridDim.x / CG;
-    constexpr int kHaloABytes = L::kABytes;
+    constexpr int kHaloABytes = L::kABytes;          // one halo tile
+    constexpr int kAStageBytes = NT * kHaloABytes;   // one A stage = the halo tiles of a whole tile group
     constexpr int kRowBytes = L::kRowBytes;
     const int kAStages = p.a_stages, kBStages = p.stages;
-    constexpr uint32_t kTmemCols = BN > 128 ? 512 : 2 * BN;   // (BN = 192: 384 columns used of 512)
+    constexpr uint32_t kAccCols = 2 * NT * BN;       // two groups of NT accumulators (BN = 192: 384 columns used of 512)
+    constexpr uint32_t kTmemCols = kAccCols > 256 ? 512 : (kAccCols > 128 ? 256 : (kAccCols > 64 ? 128 : 64));
 
     // 128-byte swizzle atoms need a 1024-byte aligned base: declared on the array (the dynamic window then
     // starts aligned, so no slack bytes are reserved) and checked once
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* sA = smem;                                        // [kAStages] halo tiles (180 px x 128 B, swizzled)
-    uint8_t* sB = smem + kAStages * kHaloABytes;               // [kBStages][BN][64] bf16
+    uint8_t* sA = smem;                                        // [kAStages][NT] halo tiles (180 px x 128 B, swizzled)
+    uint8_t* sB = smem + kAStages * kAStageBytes;              // [kBStages][BN][64] bf16
     uint8_t* sStage = sB + kBStages * L::kBBytes;
     const uint8_t* sW2 = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;   // chained form: W2 [BN / 64][BN][64] bf16
     // concat chain: Y[2] cat tiles, then W2a [64][64] (128-byte rows), then W2b [64][32] (64-byte rows)
@@ -1101,7 +1115,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint64_t* w2_full = res_bar + 10;
     uint64_t* y_full = res_bar + 11;      // [2] cat tile TMA -> epilogue group / second MMA chain (concat chain)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 13);
-    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0);
+    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0 && NT == 1);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -1165,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
     if (warp == 2 && p.chain) {
         // second UMMA chain of the chained 1x1 conv
-        if constexpr ((BN == 64 || BN == 128) && CG == 1) {
+        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1) {
             if (p.chain == 1 && ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
         }
         if constexpr (kCatCapable) {
@@ -1202,16 +1216,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 if (ptx::elect_one()) {
                     if (CG == 2) {
                         if (rank == 0) ptx::mbar_expect_tx(&afull[sa], 2 * L::kATxBytes);
-                        ptx::tma_load_4d_cg2(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
+                        ptx::tma_load_4d_cg2(sA + sa * kAStageBytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
                                              tc.x0 - 1, tc.y0 - 1, tc.n0);
                     } else {
-                        ptx::mbar_expect_tx(&afull[sa], L::kATxBytes);
-                        if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
-                            ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1,
-                                             tc.n0);
-                        else
-                            ptx::tma_load_4d(sA + sa * kHaloABytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
-                                             tc.x0 - 1, tc.y0 - 1, tc.n0);
+                        ptx::mbar_expect_tx(&afull[sa], NT * L::kATxBytes);
+#pragma unroll
+                        for (int sub = 0; sub < NT; ++sub) {   // the halo tiles of the group: same patch, images n0 .. n0 + NT - 1
+                            uint8_t* dst = sA + sa * kAStageBytes + sub * kHaloABytes;
+                            if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
+                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1, tc.n0 + sub);
+                            else
+                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1, tc.y0 - 1,
+                                                 tc.n0 + sub);
+                        }
                     }
                 }
                 __syncwarp();
@@ -1254,11 +1271,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 // narrow-N layers).  Slot parity of channel block g of the CTA: g & 1.
                 for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                     const int ab = it & 1;
-                    const uint32_t d_tmem = tmem_base + ab * BN;
+                    const uint32_t d_tmem = tmem_base + ab * (NT * BN);
                     const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
                     int sa = int(ga % uint32_t(kAStages));
                     uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
-                    uint32_t a_lo = a_lo0 + sa * (kHaloABytes >> 4);
+                    uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4);
                     const bool wait_b = !p.resident || it < p.issuers;
                     ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
@@ -1277,13 +1294,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                                            : (((kh * kHaloW + kw) * kARowBytes) >> 4));
                             const uint32_t b_tap = b_lo0 + tap * (L::kBBytes >> 4);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {
-                                if (CG == 2)
-                                    ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
-                                                            (cb | tap | kk) != 0);
-                                else
-                                    ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
-                                                        (cb | tap | kk) != 0);
+                            for (int sub = 0; sub < NT; ++sub) {   // the same weight tile feeds every pixel tile of the group
+#pragma unroll
+                                for (int kk = 0; kk < BK / 16; ++kk) {
+                                    if (CG == 2)
+                                        ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
+                                                                (cb | tap | kk) != 0);
+                                    else
+                                        ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
+                                                            b_tap + 2 * kk, b_hi, idesc, (cb | tap | kk) != 0);
+                                }
                             }
                             if (!p.resident) {
                                 if (CG == 2) ptx::umma_commit_cg2(&bempty[tap]);
@@ -1292,7 +1312,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         }
                         if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
                         else ptx::umma_commit(&aempty[sa]);
-                        a_lo += kHaloABytes >> 4;
+                        a_lo += kAStageBytes >> 4;
                         if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                     }
                     if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
@@ -1301,7 +1321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             } else
             for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                 const int ab = it & 1;
-                const uint32_t d_tmem = tmem_base + ab * BN;
+                const uint32_t d_tmem = tmem_base + ab * (NT * BN);
                 const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
                 int sa = int(ga % uint32_t(kAStages));
                 uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
@@ -1312,7 +1332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     sb = int(gb % uint32_t(kBStages));
                     pb = (gb / uint32_t(kBStages)) & 1u;
                 }
-                uint32_t a_lo = a_lo0 + sa * (kHaloABytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
+                uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
                 // resident weights: both issuers wait once for all nine taps (phase 0 of each slot)
                 const bool wait_b = !p.resident || it < p.issuers;   // (resident: the first tile of each issuer)
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
@@ -1330,13 +1350,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             a_lo + (S2 ? (((kh * kS2HaloW + (kw != 0 ? 1 : 0)) * 128 + (kw != 1 ? 64 : 0)) >> 4)
                                        : (((kh * kHaloW + kw) * kARowBytes) >> 4));
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk) {
-                            if (CG == 2)
-                                ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
-                                                        (cb | tap | kk) != 0);
-                            else
-                                ptx::umma_bf16_lohi(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
-                                                    (cb | tap | kk) != 0);
+                        for (int sub = 0; sub < NT; ++sub) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; ++kk) {
+                                if (CG == 2)
+                                    ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
+                                                            (cb | tap | kk) != 0);
+                                else
+                                    ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
+                                                        b_lo + 2 * kk, b_hi, idesc, (cb | tap | kk) != 0);
+                            }
                         }
                         if (!p.resident) {
                             if (CG == 2) ptx::umma_commit_cg2(&bempty[sb]);
@@ -1347,7 +1370,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     }
                     if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
                     else ptx::umma_commit(&aempty[sa]);
-                    a_lo += kHaloABytes >> 4;
+                    a_lo += kAStageBytes >> 4;
                     if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                 }
                 if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
@@ -1361,8 +1384,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 conv_epilogue_cat(p, sStage, sY, sBias, tfull_bar, tempty_bar, chain_bars, y_full, tmem_base, warp, lane);
         }
         if (p.chain != 2)
-            conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
-                                  nullptr, nullptr, chain_bars);
+            conv_epilogue<BN, CG, NT>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
+                                      nullptr, nullptr, chain_bars);
     }
 
     ptx::tc_fence_before();
@@ -1639,6 +1662,7 @@ struct ConvTcPlan {
     int bn, bk;
     int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
     int s2;                    // halo kernel in its stride-2 pixel-pair form
+    int nt = 1;                // halo kernel: pixel tiles per weight pass (ConvTcParams.nt)
     bool conv0 = false;        // the first layer on the tensor cores (conv0_tc_kernel)
     int pix_per_image_tiles;   // tiles_x * tiles_y (work items per image and N block)
 };
@@ -1812,36 +1836,60 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (cat_chain) p.epi_bufs = 2;         // b tile + output tile
     const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) +
                       (cat_chain ? kCatSmemBytes : (d.chain_w ? bn * bn * 2 : 0));
+    pl->nt = 1;
     if (pl->halo) {
-        p.a_stages = bn == 256 ? 2 : 3;
-        const int b_bytes = (bn / cg) * bk * 2;
-        const int kHaloABytes = halo_a_bytes(bk, pl->s2);
-        p.stages = (kSmemBudget - fixed - p.a_stages * kHaloABytes) / b_bytes;
-        if (p.stages > 12) p.stages = 12;
-        // exactly nine weight slots (slot == tap: the fast issue loop) if they fit beside two halo stages
+        // Shared-memory plan of the halo kernel for `nt` pixel tiles per weight pass (one A stage = the halo tiles of a
+        // whole group).  Returns false when fewer than two A stages (no load / MMA overlap) or two weight stages fit.
         static const int nine_env = getenv("WT_CONV_NINE") ? atoi(getenv("WT_CONV_NINE")) : 1;
-        if (nine_env && p.stages != 9 && 9 * b_bytes + 2 * kHaloABytes + fixed <= kSmemBudget) {
-            p.stages = 9;
-            p.a_stages = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
-            if (p.a_stages > kMaxAStages) p.a_stages = kMaxAStages;
-        }
         static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
-        p.resident = (resident_env && p.cin_blocks == 1 && p.n_blocks == 1 && p.stages >= 9) ? 1 : 0;
-        p.issuers = 1;
-        if (p.resident) {
-            p.stages = 9;   // the ring wraps once per tile: stage index == tap
-            const int spare = (kSmemBudget - fixed - 9 * b_bytes) / kHaloABytes;
-            p.a_stages = spare > kMaxAStages ? kMaxAStages : spare;
-            // (a second MMA issuer warp taking alternate tiles was measured slower and has been retired: the kernels keep
-            // the `issuers` parameter but the plan always sets 1)
+        const int b_bytes = (bn / cg) * bk * 2;
+        auto plan = [&](int nt, int epi_bufs) -> bool {
+            const int fx = fixed_smem_bytes(epi_bufs) + (cat_chain ? kCatSmemBytes : (d.chain_w ? bn * bn * 2 : 0));
+            const int a_bytes = nt * halo_a_bytes(bk, pl->s2);
+            int a_stages = nt > 1 ? 2 : (bn == 256 ? 2 : 3);
+            int stages = (kSmemBudget - fx - a_stages * a_bytes) / b_bytes;
+            if (stages > 12) stages = 12;
+            // exactly nine weight slots (slot == tap: the fast issue loop) if they fit beside two halo stages
+            if (nine_env && stages != 9 && 9 * b_bytes + 2 * a_bytes + fx <= kSmemBudget) {
+                stages = 9;
+                a_stages = (kSmemBudget - fx - 9 * b_bytes) / a_bytes;
+                if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+            }
+            const bool resident = resident_env && p.cin_blocks == 1 && p.n_blocks == 1 && stages >= 9;
+            if (resident) {
+                stages = 9;   // the ring wraps once per tile: stage index == tap
+                a_stages = (kSmemBudget - fx - 9 * b_bytes) / a_bytes;
+                if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+            }
+            if (stages < 2 || a_stages < (nt > 1 ? 2 : 1)) return false;
+            p.stages = stages;
+            p.a_stages = a_stages;
+            p.resident = resident ? 1 : 0;
+            p.epi_bufs = epi_bufs;
+            pl->nt = nt;
+            pl->smem_bytes = a_stages * a_bytes + stages * b_bytes + fx;
+            return true;
+        };
+        // tile groups: as many pixel tiles per weight pass as TMEM (2 x nt x bn columns <= 512) and shared memory allow;
+        // the chained forms keep one tile per pass (their second GEMM uses the other accumulators).  WT_CONV_NT caps it.
+        static const int nt_env = getenv("WT_CONV_NT") ? atoi(getenv("WT_CONV_NT")) : 2;
+        int nt = (cg == 1 && !d.chain_w) ? nt_env : 1;
+        if (nt != 1 && nt != 2 && nt != 4) nt = 1;
+        while (nt > 1 && (2 * nt * bn > 512 || (nt == 4 && (bn > 64 || bk != 32)))) nt >>= 1;
+        bool ok = false;
+        for (; nt >= 1 && !ok; nt >>= 1) {
+            ok = plan(nt, p.epi_bufs);
+            if (!ok && nt > 1 && p.epi_bufs == 2 && !d.chain_w) ok = plan(nt, 1);   // (a second staging buffer matters less than a second A stage)
         }
-        if (p.stages < 2) {
+        p.issuers = 1;
+        if (!ok) {
             delete pl;
             set_error("not enough shared memory for the halo weight pipeline");
             return 1;
         }
-        pl->smem_bytes = p.a_stages * kHaloABytes + p.stages * b_bytes + fixed;
+        p.nt = pl->nt;
     } else {
+        p.nt = 1;
         p.a_stages = 0;
         p.resident = 0;
         p.issuers = 1;
@@ -2062,15 +2110,15 @@ static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t
     return launch_kernel(conv_tc_kernel<BN, BK, CG>, &opt_in, prm, CG, smem, grid, stream);
 }
 
-template <int BN, int BK, int CG, int S2 = 0>
+template <int BN, int BK, int CG, int S2 = 0, int NT = 1>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static SmemOptIn opt_in;
-    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2>, &opt_in, prm, CG, smem, grid, stream);
+    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2, NT>, &opt_in, prm, CG, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
     ConvTcParams prm = pl->prm;
-    const int tiles_n = ceil_div(n_images, prm.tn);
+    const int tiles_n = ceil_div(n_images, prm.tn * prm.nt);   // (halo kernel: groups of nt images)
     prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items (CTA pairs: per pair)
     prm.n_images = n_images;
     if (prm.num_tiles == 0) return 0;
@@ -2106,32 +2154,42 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
         return 0;
     }
     if (pl->halo) {
+        const int nt = pl->nt;
         if (pl->s2) {         // 32 -> 32/64 channels, stride 2 (layer 1)
-            switch (pl->bn) {
-                case 64: return launch_halo<64, 32, 1, 1>(prm, smem, grid, stream);
-                case 32: return launch_halo<32, 32, 1, 1>(prm, smem, grid, stream);
+            switch (pl->bn * 10 + nt) {
+                case 641: return launch_halo<64, 32, 1, 1>(prm, smem, grid, stream);
+                case 321: return launch_halo<32, 32, 1, 1>(prm, smem, grid, stream);
+                case 642: return launch_halo<64, 32, 1, 1, 2>(prm, smem, grid, stream);
+                case 322: return launch_halo<32, 32, 1, 1, 2>(prm, smem, grid, stream);
             }
-            set_error("no stride-2 halo instantiation for this BN");
+            set_error("no stride-2 halo instantiation for this (BN, NT)");
             return 1;
         }
         if (pl->bk == 32) {   // 32 input channels (the 160x160 C2f bottlenecks)
-            switch (pl->bn) {
-                case 64: return launch_halo<64, 32, 1>(prm, smem, grid, stream);
-                case 32: return launch_halo<32, 32, 1>(prm, smem, grid, stream);
+            switch (pl->bn * 10 + nt) {
+                case 641: return launch_halo<64, 32, 1>(prm, smem, grid, stream);
+                case 321: return launch_halo<32, 32, 1>(prm, smem, grid, stream);
+                case 642: return launch_halo<64, 32, 1, 0, 2>(prm, smem, grid, stream);
+                case 322: return launch_halo<32, 32, 1, 0, 2>(prm, smem, grid, stream);
+                case 644: return launch_halo<64, 32, 1, 0, 4>(prm, smem, grid, stream);
+                case 324: return launch_halo<32, 32, 1, 0, 4>(prm, smem, grid, stream);
             }
-            set_error("no halo instantiation for this (BN, 32)");
+            set_error("no halo instantiation for this (BN, 32, NT)");
             return 1;
         }
-        switch (pl->bn * 10 + cg) {
-            case 2562: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
-            case 1282: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
-            case 2561: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
-            case 1921: return launch_halo<192, 64, 1>(prm, smem, grid, stream);
-            case 1281: return launch_halo<128, 64, 1>(prm, smem, grid, stream);
-            case 641:  return launch_halo<64, 64, 1>(prm, smem, grid, stream);
-            case 321:  return launch_halo<32, 64, 1>(prm, smem, grid, stream);
+        switch ((pl->bn * 10 + cg) * 10 + nt) {
+            case 25621: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
+            case 12821: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
+            case 25611: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
+            case 19211: return launch_halo<192, 64, 1>(prm, smem, grid, stream);
+            case 12811: return launch_halo<128, 64, 1>(prm, smem, grid, stream);
+            case 6411:  return launch_halo<64, 64, 1>(prm, smem, grid, stream);
+            case 3211:  return launch_halo<32, 64, 1>(prm, smem, grid, stream);
+            case 12812: return launch_halo<128, 64, 1, 0, 2>(prm, smem, grid, stream);
+            case 6412:  return launch_halo<64, 64, 1, 0, 2>(prm, smem, grid, stream);
+            case 3212:  return launch_halo<32, 64, 1, 0, 2>(prm, smem, grid, stream);
         }
-        set_error("no halo instantiation for this (BN, CG)");
+        set_error("no halo instantiation for this (BN, CG, NT)");
         return 1;
     }
     switch ((pl->bn * 100 + pl->bk) * 10 + cg) {
