@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define WT_ABI_VERSION 11
+#define WT_ABI_VERSION 12
 
 /* ------------------------------------------------------------------------------------------ */
 /* errors / info                                                                              */
@@ -288,6 +288,21 @@ int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t* cam_xywh, 
  * speed = centre difference over `period` rows / frame difference (NaN for the first `period` rows); every float column
  * rounded to 5 decimals exactly as DataFrame.round(5) does (rint(x * 1e5) / 1e5).                                       */
 int wt_analysis_columns(const double* table, int64_t n, int period, int cycle_frame_num, double* out, void* stream);
+
+/* Row masks of the analysed log (replaces DataAnalyzer.clean, wtracker/eval/data_analyzer.py:121-159, and the masks of
+ * DataAnalyzer.calc_anomalies, :326-374) over wt_analysis_columns' f64 [n][30] table:
+ *   moving   : u8 [n] phase of each row (0 imaging | 1 moving), may be NULL unless imaging_only
+ *   h_bounds : HOST pointer to (x_min, y_min, x_max, y_max) or NULL: a row survives when its finite worm box lies inside,
+ *              or when it has no prediction OR its worm box fails the x range and its microscope box lies inside (the
+ *              reference's in-place mask aliasing, :140-148; golden tests/golden/reference_masks.npz)
+ *   keep     : u8 [n] = the row survives imaging_only and bounds (trim_cycles needs the largest cycle of the SURVIVING
+ *              rows, a reduction the host mirror does on the kept cycle column)
+ *   anomaly  : u8 [n] bit 0 wrm_speed >= min_speed, 1 bbox_error >= min_bbox_error, 2 worm_deviation >= min_dist_error,
+ *              3 wrm_w >= min_size, 4 wrm_h >= min_size, 5 no_preds and the worm box is not finite
+ * Comparisons with NaN are false, as pandas evaluates them; thresholds may be +inf. */
+int wt_analysis_masks(const double* table30, const uint8_t* moving, int64_t n, int imaging_only, const double* h_bounds,
+                      int no_preds, double min_bbox_error, double min_dist_error, double min_speed, double min_size,
+                      uint8_t* keep, uint8_t* anomaly, void* stream);
 
 /* Segmentation-based tracking error (replaces ErrorCalculator.calculate_precise / calculate_segmentation,
  * wtracker/eval/error_calculator.py:19-161): for row i the fraction of the segmented worm — pixels of the

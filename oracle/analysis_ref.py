@@ -48,3 +48,37 @@ def analysis_columns(table17: np.ndarray, period: int, cycle_frame_num: int) -> 
     out[:, 12:16] = np.round(out[:, 12:16], 5)                                             # DataFrame.round(5), :69
     out[:, 18:29] = np.round(out[:, 18:29], 5)
     return out
+
+
+def clean_keep(table30: np.ndarray, moving: np.ndarray, imaging_only: bool = False, bounds=None,
+               trim_cycles: bool = False) -> np.ndarray:
+    """Rows DataAnalyzer.clean keeps (reference: wtracker/eval/data_analyzer.py:121-159), as a boolean mask."""
+    t = np.asarray(table30, dtype=np.float64)
+    keep = np.ones(len(t), dtype=bool)
+    if imaging_only:
+        keep &= ~np.asarray(moving, dtype=bool)
+    if bounds is not None:
+        wrm, mic = t[:, 12:16], t[:, 8:12]
+        has_pred = np.isfinite(wrm).all(axis=1)
+        with np.errstate(invalid="ignore"):
+            # `mask_wrm = has_pred; mask_wrm &= <x condition>` narrows has_pred in place (:140-142; the result is a Series,
+            # so the y condition of :143 does not reach has_pred): `~has_pred` at :145 is "no prediction or x range failed"
+            in_wx = has_pred & (wrm[:, 0] >= bounds[0]) & (wrm[:, 0] + wrm[:, 2] <= bounds[2])
+            in_w = in_wx & (wrm[:, 1] >= bounds[1]) & (wrm[:, 1] + wrm[:, 3] <= bounds[3])
+            in_m = ~in_wx & (mic[:, 0] >= bounds[0]) & (mic[:, 0] + mic[:, 2] <= bounds[2]) & (mic[:, 1] >= bounds[1]) & \
+                (mic[:, 1] + mic[:, 3] <= bounds[3])
+        keep &= in_w | in_m
+    if trim_cycles and keep.any():
+        cyc = t[:, 1]
+        keep &= (cyc != 0) & (cyc != cyc[keep].max())                                     # :150-153
+    return keep
+
+
+def anomaly_bits(table30: np.ndarray, no_preds=True, min_bbox_error=np.inf, min_dist_error=np.inf, min_speed=np.inf,
+                 min_size=np.inf) -> np.ndarray:
+    """calc_anomalies' six masks (:349-361) packed as bits 0..5: speed, bbox error, distance, width, height, no prediction."""
+    t = np.asarray(table30, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        flags = [t[:, 24] >= min_speed, t[:, 28] >= min_bbox_error, t[:, 27] >= min_dist_error, t[:, 14] >= min_size,
+                 t[:, 15] >= min_size, (~np.isfinite(t[:, 12:16]).all(axis=1)) & bool(no_preds)]
+    return sum((f.astype(np.uint8) << i) for i, f in enumerate(flags)).astype(np.uint8)

@@ -12,7 +12,7 @@ def test_header_symbols_are_exported(native_lib):
     header = (ROOT / "include" / "wtracker_b200.h").read_text()
     declared = set(re.findall(r"\b(wt_[a-z0-9_]+)\s*\(", header))
     declared -= {"wt_engine"}
-    assert len(declared) == 25
+    assert len(declared) == 26
     from wtracker_b200 import _lib
 
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)

@@ -50,6 +50,11 @@ CASES = [
     (9, 40, 40, 256, 64, 3, 1, 1, 0, 0),
     (33, 80, 80, 128, 128, 3, 1, 1, 1, 0),   # ~11 groups per CTA, streamed weights, residual
     (6, 80, 80, 128, 192, 3, 1, 1, 0, 0),    # BN 192: one tile per pass
+    # 40 x 40 maps: 8 x 8 tiles of two interleaved images (odd batches: a phantom second image)
+    (5, 40, 40, 128, 128, 3, 1, 1, 1, 0),
+    (4, 40, 40, 256, 192, 3, 1, 1, 0, 0),
+    (7, 40, 40, 64, 64, 3, 1, 1, 1, 0),
+    (64, 40, 40, 128, 128, 3, 1, 1, 1, 0),
 ]
 
 # chained conv + 1x1 (wt_selftest_conv_chain): batch, h, w, cin, cout, k, stride

@@ -4,10 +4,10 @@ tag=${1:-x}
 mkdir -p gpurun_out
 timeout 400 python tools/gpu_conv_selftest.py > gpurun_out/selftest_$tag.log 2>&1; tail -1 gpurun_out/selftest_$tag.log
 grep -v "^\[OK\]" gpurun_out/selftest_$tag.log | head -8
-for v in "1 0" "2 0" "4 0" "2 1" "4 1"; do
+for v in "1 0" "4 0" "1 1" "4 1"; do
   set -- $v
-  WT_CONV_NT=$1 WT_EPI_BUFS=$2 timeout 90 python tools/gpu_layer_times.py 64 640 > gpurun_out/layers_${tag}_nt$1_e$2.log 2>&1 || echo "layer times nt$1 e$2 FAILED"
-  echo "nt=$1 epi=$2: $(head -1 gpurun_out/layers_${tag}_nt$1_e$2.log)"
+  WT_CONV_NT=$1 WT_CONV_IL=$2 timeout 90 python tools/gpu_layer_times.py 64 640 > gpurun_out/layers_${tag}_nt$1_il$2.log 2>&1 || echo "layer times nt$1 il$2 FAILED"
+  echo "nt=$1 il=$2: $(head -1 gpurun_out/layers_${tag}_nt$1_il$2.log)"
 done
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 2>&1 | tail -25 > gpurun_out/tests_$tag.log; tail -4 gpurun_out/tests_$tag.log
 timeout 600 python bench.py --no-extras --no-cpu-baseline > gpurun_out/bench_$tag.log 2> gpurun_out/bench_$tag.err || { echo "bench FAILED"; tail -5 gpurun_out/bench_$tag.err; }

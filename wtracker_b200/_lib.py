@@ -18,7 +18,7 @@ WT_ACT_NONE, WT_ACT_SILU = 0, 1
 WT_DT_BF16, WT_DT_F32, WT_DT_U8 = 0, 1, 2
 
 
-ABI_VERSION = 11  # WT_ABI_VERSION of include/wtracker_b200.h this binding was written for
+ABI_VERSION = 12  # WT_ABI_VERSION of include/wtracker_b200.h this binding was written for
 
 class WtLetterbox(C.Structure):
     _fields_ = [
@@ -124,6 +124,8 @@ SIGNATURES = {
     "wt_bbox_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_mse_error": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_analysis_columns": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wt_analysis_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double,
+                                    C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wt_precise_error": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
     "wt_log_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,

@@ -58,8 +58,71 @@ __global__ void analysis_columns_kernel(const double* __restrict__ in, long long
     o[29] = nan;
 }
 
+// Row masks of DataAnalyzer.clean (keep) and DataAnalyzer.calc_anomalies (six flag bits) over the analysed table.
+struct MaskParams {
+    int imaging_only, has_bounds, no_preds;
+    double b0, b1, b2, b3;
+    double min_bbox_error, min_dist_error, min_speed, min_size;
+};
+
+__global__ void analysis_masks_kernel(const double* __restrict__ table30, const uint8_t* __restrict__ moving, long long n,
+                                      const MaskParams m, uint8_t* __restrict__ keep, uint8_t* __restrict__ anomaly) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = table30 + i * 30;
+    const double mx = r[8], my = r[9], mw = r[10], mh = r[11];
+    const double wx = r[12], wy = r[13], ww = r[14], wh = r[15];
+    const bool has_pred = isfinite(wx) && isfinite(wy) && isfinite(ww) && isfinite(wh);
+    bool k = true;
+    if (m.imaging_only && moving[i]) k = false;
+    if (m.has_bounds) {
+        // The reference means "a frame with a prediction is judged by its worm box, a frame without one by the
+        // microscope box", but `mask_wrm = has_pred; mask_wrm &= <x condition>` narrows has_pred IN PLACE (one ndarray,
+        // two names; the result comes back as a pandas Series, so the second `&=` with the y condition no longer
+        // touches has_pred — data_analyzer.py:140-148 under numpy 2 / pandas 2).  Hence `mask_mic = ~has_pred` means
+        // "no prediction, or the worm box fails the X range": such rows are judged by the microscope box.  Kept as is
+        // (results must be the reference's; golden: tests/golden/reference_masks.npz).  NaN comparisons are false.
+        const bool in_wx = has_pred && wx >= m.b0 && __dadd_rn(wx, ww) <= m.b2;
+        const bool in_wrm = in_wx && wy >= m.b1 && __dadd_rn(wy, wh) <= m.b3;
+        const bool in_mic = !in_wx && mx >= m.b0 && __dadd_rn(mx, mw) <= m.b2 && my >= m.b1 && __dadd_rn(my, mh) <= m.b3;
+        k = k && (in_wrm || in_mic);
+    }
+    keep[i] = k ? 1 : 0;
+    uint8_t a = 0;
+    if (r[24] >= m.min_speed) a |= 1;         // wrm_speed
+    if (r[28] >= m.min_bbox_error) a |= 2;    // bbox_error
+    if (r[27] >= m.min_dist_error) a |= 4;    // worm_deviation
+    if (ww >= m.min_size) a |= 8;
+    if (wh >= m.min_size) a |= 16;
+    if (m.no_preds && !has_pred) a |= 32;
+    anomaly[i] = a;
+}
+
 }  // namespace
 }  // namespace wt
+
+extern "C" int wt_analysis_masks(const double* table30, const uint8_t* moving, int64_t n, int imaging_only,
+                                 const double* h_bounds, int no_preds, double min_bbox_error, double min_dist_error,
+                                 double min_speed, double min_size, uint8_t* keep, uint8_t* anomaly, void* stream) {
+    using namespace wt;
+    if (n == 0) return 0;
+    WT_REQUIRE(table30 && keep && anomaly, "null argument");
+    WT_REQUIRE(!imaging_only || moving, "imaging_only needs the phase column");
+    MaskParams m;
+    m.imaging_only = imaging_only;
+    m.has_bounds = h_bounds != nullptr;
+    m.no_preds = no_preds;
+    m.b0 = m.b1 = m.b2 = m.b3 = 0.0;
+    if (h_bounds) { m.b0 = h_bounds[0]; m.b1 = h_bounds[1]; m.b2 = h_bounds[2]; m.b3 = h_bounds[3]; }
+    m.min_bbox_error = min_bbox_error;
+    m.min_dist_error = min_dist_error;
+    m.min_speed = min_speed;
+    m.min_size = min_size;
+    analysis_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table30, moving, n, m,
+                                                                                                 keep, anomaly);
+    WT_LAUNCHED();
+    return 0;
+}
 
 extern "C" int wt_analysis_columns(const double* table, int64_t n, int period, int cycle_frame_num, double* out,
                                    void* stream) {

@@ -102,6 +102,9 @@ struct ConvTcParams {
     // 3x3 layers are bound by the L2 -> shared-memory fill, ~86 % of it weights: DESIGN.md), nt accumulators sit side
     // by side in TMEM and an epilogue group drains all of them.
     int nt;
+    // halo kernel: images interleaved per tile (IL template parameter, 1 | 2).  il == 2: the output / residual tensor maps
+    // list (channel, x, image, row), the tile is tw x th x 2 with th = 8.
+    int il;
 };
 
 template <int BN, int BK>
@@ -238,8 +241,14 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
         ptx::bar_sync(bar_id, kEpiThreads);   // (the slot is rewritten two work items of this group later: one more barrier in between)
         if (h == 0) {
             const int px = tc.x0 + row % p.tw;
-            const int py = tc.y0 + (row / p.tw) % p.th;
-            const int pn = tc.n0 + sub + row / (p.tw * p.th);
+            int py, pn;
+            if (p.il == 2) {   // row = (ty * 2 + img) * 8 + tx
+                py = tc.y0 + (row >> 4);
+                pn = tc.n0 + 2 * sub + ((row >> 3) & 1);
+            } else {
+                py = tc.y0 + (row / p.tw) % p.th;
+                pn = tc.n0 + sub * p.tn + row / (p.tw * p.th);
+            }
             if (px < p.out_w && py < p.out_h && pn < p.n_images)
                 p.dot_out[(size_t(pn) * p.out_h + py) * p.out_w + px] = (dot + slot[row]) + dw[p.cout];
         }
@@ -299,7 +308,8 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
         for (int su = 0; su < NT * kUnits; ++su) {
             const int sub = NT == 1 ? 0 : su / kUnits;          // pixel tile of the group (image n0 + sub)
             const int unit = NT == 1 ? su : su - sub * kUnits;
-            const int n0s = n0 + sub;
+            const int n0s = n0 + sub * p.tn;
+            const int cy = p.il == 2 ? n0s : y0, cn = p.il == 2 ? y0 : n0s;   // tensor-map order of the last two coordinates
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * NT + sub) * BN + h * CW;
             const int sb = two_bufs ? (unit_counter & 1) : 0;
             uint8_t* stage_buf = sStage + sb * kStageBufBytes;
@@ -313,7 +323,7 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             ptx::bar_sync(bar_id, kEpiThreads);
             if (p.has_res && store_thread) {
                 ptx::mbar_expect_tx(&res_bar[sb], unit_bytes);
-                ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, y0, n0s);
+                ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, cy, cn);
             }
             ptx::tmem_ld_wait();
             if (su == NT * kUnits - 1) {
@@ -434,7 +444,7 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             ptx::fence_proxy_async_smem();
             ptx::bar_sync(bar_id, kEpiThreads);
             if (store_thread) {
-                ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * kUnitCh, x0, y0, n0s);
+                ptx::tma_store_4d(&p.tmD, stage_buf, p.dst_coff + nblk * BN + unit * kUnitCh, x0, cy, cn);
                 ptx::tma_store_commit();
             }
             ++unit_counter;
@@ -1058,27 +1068,37 @@ constexpr int kHaloW = 10, kHaloH = 18;
 // and a stride of two patch rows (18 rows) between tile rows.  One fill instead of nine strided ones.
 constexpr int kS2HaloW = 9, kS2HaloH = 33;
 // bytes of one halo stage (1024-byte aligned): S2 = 0: K block of BK channels (rows of 2 * BK bytes)
-__host__ __device__ constexpr int halo_rows(int s2) { return s2 ? kS2HaloW * kS2HaloH : kHaloW * kHaloH; }
-__host__ __device__ constexpr int halo_a_bytes(int bk, int s2) {
-    return ((halo_rows(s2) * (s2 ? 128 : bk * 2) + 1023) / 1024) * 1024;
+// Interleaved form (IL = 2): the tile is 8 columns x 8 rows of TWO images, held in shared memory as [row][image][x]
+// (the tensor maps list the image dimension before the row dimension), so accumulator row group 2 * ty + img is still
+// kHaloW pixels after the previous one — the same descriptor stride — and tap (kh, kw) starts (kh * 2 * kHaloW + kw)
+// pixels in.  Maps whose height is a multiple of 8 but not of 16 (40 x 40) tile exactly instead of wasting a fifth of
+// every third tile row.
+constexpr int kIlHaloRows = 10 * 2 * kHaloW;   // (8 + 2) rows x 2 images x 10 pixels
+__host__ __device__ constexpr int halo_rows(int s2, int il = 1) {
+    return s2 ? kS2HaloW * kS2HaloH : (il == 2 ? kIlHaloRows : kHaloW * kHaloH);
+}
+__host__ __device__ constexpr int halo_a_bytes(int bk, int s2, int il = 1) {
+    return ((halo_rows(s2, il) * (s2 ? 128 : bk * 2) + 1023) / 1024) * 1024;
 }
 
-template <int BN, int BK, int CG, int S2>
+template <int BN, int BK, int CG, int S2, int IL = 1>
 struct HaloSmem {
     static constexpr int kRowBytes = BK * 2;                 // weight rows: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
     static constexpr int kARowBytes = S2 ? 128 : BK * 2;     // halo rows (S2: a pixel pair)
-    static constexpr int kABytes = halo_a_bytes(BK, S2);
-    static constexpr int kATxBytes = halo_rows(S2) * kARowBytes;
+    static constexpr int kABytes = halo_a_bytes(BK, S2, IL);
+    static constexpr int kATxBytes = halo_rows(S2, IL) * kARowBytes;
     static constexpr int kBBytes = (BN / CG) * kRowBytes;    // a CTA of a pair holds BN / 2 weight rows
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN, int BK, int CG, int S2, int NT>
+template <int BN, int BK, int CG, int S2, int NT, int IL>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
     static_assert(!S2 || (BK == 32 && CG == 1), "the stride-2 pair form is written for 32 input channels");
+    static_assert(IL == 1 || (IL == 2 && !S2 && CG == 1), "interleaved tiles: stride 1, single-CTA MMAs");
     static_assert(NT == 1 || (CG == 1 && 2 * NT * BN <= 512), "tile groups: single-CTA MMAs, 2 x NT accumulators in TMEM");
-    using L = HaloSmem<BN, BK, CG, S2>;
+    using L = HaloSmem<BN, BK, CG, S2, IL>;
     constexpr int kARowBytes = L::kARowBytes;
+    constexpr int kTapRowPitch = kHaloW * IL;        // pixels between vertically adjacent taps in the halo tile
     const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
     const int first = blockIdx.x / CG, step = gridDim.x / CG;
     constexpr int kHaloABytes = L::kABytes;          // one halo tile
@@ -1115,7 +1135,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint64_t* w2_full = res_bar + 10;
     uint64_t* y_full = res_bar + 11;      // [2] cat tile TMA -> epilogue group / second MMA chain (concat chain)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 13);
-    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0 && NT == 1);
+    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0 && NT == 1 && IL == 1);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -1179,7 +1199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
     if (warp == 2 && p.chain) {
         // second UMMA chain of the chained 1x1 conv
-        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1) {
+        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1 && IL == 1) {
             if (p.chain == 1 && ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
         }
         if constexpr (kCatCapable) {
@@ -1225,6 +1245,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             uint8_t* dst = sA + sa * kAStageBytes + sub * kHaloABytes;
                             if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
                                 ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1, tc.n0 + sub);
+                            else if (IL == 2)   // (channel, x, image, row): two images per tile
+                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1,
+                                                 tc.n0 + 2 * sub, tc.y0 - 1);
                             else
                                 ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1, tc.y0 - 1,
                                                  tc.n0 + sub);
@@ -1291,7 +1314,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             const int kh = tap / 3, kw = tap - kh * 3;
                             const uint32_t a_tap =
                                 a_lo + (S2 ? (((kh * kS2HaloW + (kw != 0 ? 1 : 0)) * 128 + (kw != 1 ? 64 : 0)) >> 4)
-                                           : (((kh * kHaloW + kw) * kARowBytes) >> 4));
+                                           : (((kh * kTapRowPitch + kw) * kARowBytes) >> 4));
                             const uint32_t b_tap = b_lo0 + tap * (L::kBBytes >> 4);
 #pragma unroll
                             for (int sub = 0; sub < NT; ++sub) {   // the same weight tile feeds every pixel tile of the group
@@ -1348,7 +1371,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         const int kh = tap / 3, kw = tap - kh * 3;
                         const uint32_t a_tap =
                             a_lo + (S2 ? (((kh * kS2HaloW + (kw != 0 ? 1 : 0)) * 128 + (kw != 1 ? 64 : 0)) >> 4)
-                                       : (((kh * kHaloW + kw) * kARowBytes) >> 4));
+                                       : (((kh * kTapRowPitch + kw) * kARowBytes) >> 4));
 #pragma unroll
                         for (int sub = 0; sub < NT; ++sub) {
 #pragma unroll
@@ -1663,6 +1686,7 @@ struct ConvTcPlan {
     int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
     int s2;                    // halo kernel in its stride-2 pixel-pair form
     int nt = 1;                // halo kernel: pixel tiles per weight pass (ConvTcParams.nt)
+    int il = 1;                // halo kernel: images interleaved per tile (ConvTcParams.il)
     bool conv0 = false;        // the first layer on the tensor cores (conv0_tc_kernel)
     int pix_per_image_tiles;   // tiles_x * tiles_y (work items per image and N block)
 };
@@ -1792,9 +1816,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         bk = d.cin % 64 == 0 ? 64 : 32;
         pl->bk = bk;
         pl->s2 = halo_s2 ? 1 : 0;
+        // 8 x 16 tiles of one image, or — where 16-row tiles would hang over the map (40 x 40) — 8 x 8 tiles of two
+        // images interleaved row by row (WT_CONV_IL=0 switches the second form off for A/B runs)
+        static const int il_env = getenv("WT_CONV_IL") ? atoi(getenv("WT_CONV_IL")) : 1;
+        pl->il = (il_env && !halo_s2 && cg == 1 && !d.chain_w && bk == 64 && (bn == 64 || bn == 128 || bn == 192) &&
+                  ho % 16 != 0 && ho % 8 == 0) ? 2 : 1;
         p.tw = 8;
-        p.th = 16;
-        p.tn = 1;
+        p.th = 16 / pl->il;
+        p.tn = pl->il;
     } else {
         choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
     }
@@ -1845,7 +1874,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const int b_bytes = (bn / cg) * bk * 2;
         auto plan = [&](int nt, int epi_bufs) -> bool {
             const int fx = fixed_smem_bytes(epi_bufs) + (cat_chain ? kCatSmemBytes : (d.chain_w ? bn * bn * 2 : 0));
-            const int a_bytes = nt * halo_a_bytes(bk, pl->s2);
+            const int a_bytes = nt * halo_a_bytes(bk, pl->s2, pl->il);
             int a_stages = nt > 1 ? 2 : (bn == 256 ? 2 : 3);
             int stages = (kSmemBudget - fx - a_stages * a_bytes) / b_bytes;
             if (stages > 12) stages = 12;
@@ -1872,15 +1901,35 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         };
         // tile groups: as many pixel tiles per weight pass as TMEM (2 x nt x bn columns <= 512) and shared memory allow;
         // the chained forms keep one tile per pass (their second GEMM uses the other accumulators).  WT_CONV_NT caps it.
-        static const int nt_env = getenv("WT_CONV_NT") ? atoi(getenv("WT_CONV_NT")) : 2;
-        int nt = (cg == 1 && !d.chain_w) ? nt_env : 1;
-        if (nt != 1 && nt != 2 && nt != 4) nt = 1;
-        while (nt > 1 && (2 * nt * bn > 512 || (nt == 4 && (bn > 64 || bk != 32)))) nt >>= 1;
+        static const int nt_env = getenv("WT_CONV_NT") ? atoi(getenv("WT_CONV_NT")) : 4;
+        int nt_max = (cg == 1 && !d.chain_w) ? nt_env : 1;
+        if (nt_max != 1 && nt_max != 2 && nt_max != 4) nt_max = 1;
+        // Among the feasible group sizes take the one with the fewest tile-times on this GPU: groups are dealt to the
+        // SMs in waves, so a bigger group can cost a partly empty last wave (960 tiles on 148 SMs: 7 waves of single
+        // tiles, but 4 waves of pairs = 8 tile-times); ties go to the bigger group (less weight traffic, fewer barriers).
         bool ok = false;
-        for (; nt >= 1 && !ok; nt >>= 1) {
-            ok = plan(nt, p.epi_bufs);
-            if (!ok && nt > 1 && p.epi_bufs == 2 && !d.chain_w) ok = plan(nt, 1);   // (a second staging buffer matters less than a second A stage)
+        double best_cost = 0.0;
+        int best_nt = 0, best_epi = 0;
+        const int epi0 = p.epi_bufs;
+        for (int nt = nt_max; nt >= 1; nt >>= 1) {
+            if (nt > 1 && (2 * nt * bn > 512 || (nt == 4 && (bn > 64 || bk != 32)))) continue;
+            int epi = epi0;
+            bool fits = plan(nt, epi);
+            if (!fits && nt > 1 && epi0 == 2 && !d.chain_w) {   // (a second staging buffer matters less than a second A stage)
+                epi = 1;
+                fits = plan(nt, epi);
+            }
+            if (!fits) continue;
+            const long long groups = (long long)p.tiles_x * p.tiles_y * ceil_div(d.batch, p.tn * nt) * p.n_blocks;
+            const double cost = double((groups + sm_count - 1) / sm_count) * nt * (nt == 4 ? 0.94 : (nt == 2 ? 0.97 : 1.0));
+            if (!ok || cost < best_cost) {
+                ok = true;
+                best_cost = cost;
+                best_nt = nt;
+                best_epi = epi;
+            }
         }
+        if (ok) plan(best_nt, best_epi);
         p.issuers = 1;
         if (!ok) {
             delete pl;
@@ -1888,8 +1937,10 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
             return 1;
         }
         p.nt = pl->nt;
+        p.il = pl->il;
     } else {
         p.nt = 1;
+        p.il = 1;
         p.a_stages = 0;
         p.resident = 0;
         p.issuers = 1;
@@ -1909,6 +1960,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const uint64_t str[3] = {128, uint64_t(d.src.w) * 64, uint64_t(d.src.w) * 64 * d.src.h};
         const uint32_t box[4] = {64, kS2HaloW, kS2HaloH, 1};
         rc |= encode_tmap(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.src.base, dims, str, box, 128);
+        for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    } else if (pl->halo && pl->il == 2) {
+        // (channel, x, image, row): a box is the (8 + 2) x (8 + 2) halo of TWO images, rows of the two images alternating
+        const uint64_t img = uint64_t(d.src.ctot) * 2 * d.src.w * d.src.h, row = uint64_t(d.src.ctot) * 2 * d.src.w;
+        const uint64_t dims[4] = {uint64_t(d.src.coff + d.cin), uint64_t(d.src.w), uint64_t(d.batch), uint64_t(d.src.h)};
+        const uint64_t str[3] = {uint64_t(d.src.ctot) * 2, img, row};
+        const uint32_t box[4] = {uint32_t(bk), kHaloW, 2, 10};
+        rc |= encode_tmap(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.src.base, dims, str, box, sw_in);
         for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
     } else if (d.stride == 1) {
         // the channel extent ends with the slice, so a K block wider than the slice is zero-filled
@@ -1988,10 +2047,11 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         const int es = out_f32 ? 4 : 2;
         const int unit_ch = out_f32 ? 32 : ((bn == 32 && !cat_chain) ? 32 : 64);   // (concat chain: 64 output channels)
         const int sw = unit_ch * es;   // 128 or 64
-        const uint64_t dims[4] = {uint64_t(d.dst.ctot), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
-        const uint64_t str[3] = {uint64_t(d.dst.ctot) * es, uint64_t(d.dst.ctot) * es * wo,
-                                 uint64_t(d.dst.ctot) * es * wo * ho};
-        const uint32_t box[4] = {uint32_t(unit_ch), uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+        const bool il2 = pl->halo && pl->il == 2;   // (channel, x, image, row) instead of (channel, x, row, image)
+        const uint64_t drow = uint64_t(d.dst.ctot) * es * wo, dimg = drow * ho;
+        const uint64_t dims[4] = {uint64_t(d.dst.ctot), uint64_t(wo), uint64_t(il2 ? d.batch : ho), uint64_t(il2 ? ho : d.batch)};
+        const uint64_t str[3] = {uint64_t(d.dst.ctot) * es, il2 ? dimg : drow, il2 ? drow : dimg};
+        const uint32_t box[4] = {uint32_t(unit_ch), uint32_t(p.tw), uint32_t(il2 ? p.tn : p.th), uint32_t(il2 ? p.th : p.tn)};
         rc |= encode_tmap(&p.tmD, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                           d.dst.base, dims, str, box, sw);
         if (d.res.base) {
@@ -1999,9 +2059,10 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
                 set_error("residual must be a bf16 buffer of the output's spatial size");
                 rc = 1;
             } else {
-                const uint64_t rdims[4] = {uint64_t(d.res.ctot), uint64_t(wo), uint64_t(ho), uint64_t(d.batch)};
-                const uint64_t rstr[3] = {uint64_t(d.res.ctot) * 2, uint64_t(d.res.ctot) * 2 * wo,
-                                          uint64_t(d.res.ctot) * 2 * wo * ho};
+                const uint64_t rrow = uint64_t(d.res.ctot) * 2 * wo, rimg = rrow * ho;
+                const uint64_t rdims[4] = {uint64_t(d.res.ctot), uint64_t(wo), uint64_t(il2 ? d.batch : ho),
+                                           uint64_t(il2 ? ho : d.batch)};
+                const uint64_t rstr[3] = {uint64_t(d.res.ctot) * 2, il2 ? rimg : rrow, il2 ? rrow : rimg};
                 rc |= encode_tmap(&p.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.res.base, rdims, rstr, box, sw);
             }
         } else {
@@ -2041,6 +2102,8 @@ int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* 
     p.out_w = wo; p.out_h = ho;
     p.epi_bufs = 2;
     p.issuers = 1;
+    p.nt = 1;
+    p.il = 1;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     pl->smem_bytes = kC0AStages * kC0ABytes + kEpiGroups * 4 * kStageBufBytes + 2048 + kC0RawStages * kC0RawBytes + 256 +
                      kBarrierBytes;
@@ -2110,10 +2173,10 @@ static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t
     return launch_kernel(conv_tc_kernel<BN, BK, CG>, &opt_in, prm, CG, smem, grid, stream);
 }
 
-template <int BN, int BK, int CG, int S2 = 0, int NT = 1>
+template <int BN, int BK, int CG, int S2 = 0, int NT = 1, int IL = 1>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static SmemOptIn opt_in;
-    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2, NT>, &opt_in, prm, CG, smem, grid, stream);
+    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2, NT, IL>, &opt_in, prm, CG, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
@@ -2177,7 +2240,7 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
             set_error("no halo instantiation for this (BN, 32, NT)");
             return 1;
         }
-        switch ((pl->bn * 10 + cg) * 10 + nt) {
+        if (pl->il == 1) switch ((pl->bn * 10 + cg) * 10 + nt) {
             case 25621: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
             case 12821: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
             case 25611: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
@@ -2188,6 +2251,15 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
             case 12812: return launch_halo<128, 64, 1, 0, 2>(prm, smem, grid, stream);
             case 6412:  return launch_halo<64, 64, 1, 0, 2>(prm, smem, grid, stream);
             case 3212:  return launch_halo<32, 64, 1, 0, 2>(prm, smem, grid, stream);
+        }
+        if (pl->il == 2 && cg == 1) {   // two images per tile (40 x 40 maps)
+            switch (pl->bn * 10 + nt) {
+                case 1921: return launch_halo<192, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
+                case 1281: return launch_halo<128, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
+                case 641:  return launch_halo<64, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
+                case 1282: return launch_halo<128, 64, 1, 0, 2, 2>(prm, smem, grid, stream);
+                case 642:  return launch_halo<64, 64, 1, 0, 2, 2>(prm, smem, grid, stream);
+            }
         }
         set_error("no halo instantiation for this (BN, CG, NT)");
         return 1;
