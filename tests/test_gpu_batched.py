@@ -93,7 +93,7 @@ def test_lockstep_yolo_equals_separate_simulators(video, K):
         assert np.array_equal(table[: len(logged), e], want, equal_nan=True)
         assert np.isnan(table[len(logged):, e]).all()
     assert np.isfinite(table[:9]).all(), "the synthetic worm is detected in the first cycle"
-    assert len({tuple(v) for v in res["pos_trace"][-1]}) == K or K == 1
+    assert len({tuple(v) for v in res["pos_trace"][0]}) == K      # different starts (they converge on the same worm)
 
 
 def test_lockstep_mlp_equals_separate_simulators(golden):

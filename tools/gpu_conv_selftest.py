@@ -55,6 +55,11 @@ CASES = [
     (4, 40, 40, 256, 192, 3, 1, 1, 0, 0),
     (7, 40, 40, 64, 64, 3, 1, 1, 1, 0),
     (64, 40, 40, 128, 128, 3, 1, 1, 1, 0),
+    # 1x1 convs with the weights of an N block resident in shared memory
+    (64, 40, 40, 512, 256, 1, 1, 1, 0, 0),
+    (8, 40, 40, 384, 256, 1, 1, 1, 0, 0),
+    (3, 40, 40, 256, 256, 1, 1, 0, 0, 1),    # f32 output
+    (5, 80, 80, 256, 128, 1, 1, 1, 0, 0),
 ]
 
 # chained conv + 1x1 (wt_selftest_conv_chain): batch, h, w, cin, cout, k, stride

@@ -813,8 +813,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint8_t* smem = smem_raw;
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;                                  // [stages][128][BK] bf16 (swizzled)
-    uint8_t* sB = smem + kStages * L::kABytes;           // [stages][BN][BK]  bf16 (swizzled)
-    uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 groups x epi_bufs x 16 KB epilogue staging
+    // 1x1 convs whose whole K extent of one N block fits (ConvTcParams.resident): B holds all cin_blocks K blocks of the
+    // CTA's N block, loaded once; the ring then carries A tiles only
+    const int kBSlots = p.resident ? p.cin_blocks : kStages;
+    uint8_t* sB = smem + kStages * L::kABytes;           // [stages | cin_blocks][BN][BK]  bf16 (swizzled)
+    uint8_t* sStage = sB + kBSlots * L::kBBytes;         // 2 groups x epi_bufs x 16 KB epilogue staging
     // addend patches [2 groups][BN / 32][32 px][128 B], 1024-byte aligned like everything before them (128-byte swizzle)
     const uint8_t* sAdd = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;
     float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sAdd) + (p.has_add ? add_smem_bytes(BN) : 0) +
@@ -930,6 +933,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int kb = 0; kb < BN / 64; ++kb)
                 ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
         }
+        if (p.resident && first < p.num_tiles && ptx::elect_one()) {
+            // weights are constants: loaded before the grid dependency resolves.  Every tile of this CTA has the same N
+            // block (the host only sets `resident` when the tile stride is a multiple of n_blocks).
+            const int nblk0 = decode_tile<CG>(p, first, rank).nblk;
+            ptx::mbar_expect_tx(w2_full, p.cin_blocks * L::kBBytes);
+            for (int cb = 0; cb < p.cin_blocks; ++cb)
+                ptx::tma_load_2d(sB + cb * L::kBBytes, &p.tmB, w2_full, cb * BK, nblk0 * BN);
+        }
         __syncwarp();
         ptx::grid_dependency_wait();
         int stage = 0;
@@ -960,6 +971,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                                  p.src_coff + cb * BK, ax, ay, n0);
                             ptx::tma_load_2d_cg2(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage],
                                                  tap * p.cin + cb * BK, nblk * BN + rank * (BN / 2));
+                        } else if (p.resident) {
+                            ptx::mbar_expect_tx(&full_bar[stage], L::kABytes);
+                            ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                             p.src_coff + cb * BK, ax, ay, n0);
                         } else {
                             ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
                             ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
@@ -991,13 +1006,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = w;
+            if (p.resident && first < p.num_tiles) {
+                ptx::mbar_wait(w2_full, 0);
+                ptx::tc_fence_after();
+            }
             for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
                 const uint32_t g0 = uint32_t(it) * uint32_t(num_kb);
                 int stage = int(g0 % uint32_t(kStages));
                 uint32_t phase = (g0 / uint32_t(kStages)) & 1u;
-                uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
+                uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = p.resident ? b_lo0 : b_lo0 + stage * (L::kBBytes >> 4);
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -1016,12 +1035,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (CG == 2) ptx::umma_commit_cg2(&empty_bar[stage]);
                     else ptx::umma_commit(&empty_bar[stage]);
                     a_lo += L::kABytes >> 4;
-                    b_lo += L::kBBytes >> 4;
+                    b_lo += L::kBBytes >> 4;   // (resident: K block kb of the resident set; restarts with the next tile)
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                         a_lo = a_lo0;
-                        b_lo = b_lo0;
+                        if (!p.resident) b_lo = b_lo0;
                     }
                 }
                 if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);   // accumulator complete (both CTAs' epilogues)
@@ -1948,6 +1967,24 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         p.stages = (kSmemBudget - fixed) / stage_bytes;
         if (p.stages > kMaxStages) p.stages = kMaxStages;
         pl->smem_bytes = p.stages * stage_bytes + fixed;
+        // 1x1 convs: the K extent of one N block resident in shared memory (loaded once per CTA instead of once per
+        // pixel tile; these layers are bound by the L2 -> shared-memory fill, two thirds of it weights) when at least four
+        // A stages still fit and every tile of a CTA has the same N block (148 SMs: n_blocks 1 | 2 | 4).
+        static const int res1_env = getenv("WT_CONV_RES1") ? atoi(getenv("WT_CONV_RES1")) : 1;
+        if (res1_env && d.k == 1 && cg == 1 && !d.chain_w && !d.dot_w && sm_count % p.n_blocks == 0) {
+            const int b_res = p.cin_blocks * bn * bk * 2, a_bytes = kTileM * bk * 2;
+            for (int epi = p.epi_bufs; epi >= 1; --epi) {
+                const int fx = fixed_smem_bytes(epi) + (d.add.base ? add_smem_bytes(bn) : 0);
+                const int a_stages = (kSmemBudget - fx - b_res) / a_bytes;
+                if (a_stages >= 4) {
+                    p.resident = 1;
+                    p.epi_bufs = epi;
+                    p.stages = a_stages > kMaxStages ? kMaxStages : a_stages;
+                    pl->smem_bytes = p.stages * a_bytes + b_res + fx;
+                    break;
+                }
+            }
+        }
     }
 
     const int sw_in = bk * 2;   // swizzle span == K-block row bytes

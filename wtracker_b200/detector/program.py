@@ -64,7 +64,9 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     if chain_exit is None:        # the C2f-exit concat chain follows `chain` unless switched off (WT_CHAIN_EXIT=0)
         import os
         chain_exit = chain and os.environ.get("WT_CHAIN_EXIT", "1") != "0"
-    assert arch.nc == 1, "the fused class-logit path is written for single-class models (reference: single_cls)"
+    if arch.nc != 1:
+        raise NotImplementedError(f"the CUDA detector is built for single-class checkpoints (the reference trains with "
+                                  f"single_cls: True, yolo_train_config.yaml:27); this one has nc = {arch.nc}")
     p = Program(arch, net_h, net_w)
     specs = {s.name: s for s in arch.conv_specs()}
     c = arch.c

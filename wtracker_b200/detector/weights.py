@@ -21,7 +21,8 @@ CALIB_PATH = Path(__file__).resolve().parents[2] / "models" / "synthetic_yolov8s
 # --------------------------------------------------------------------------------------------
 # synthetic weights
 # --------------------------------------------------------------------------------------------
-def synthetic_state_dict(seed: int = 0, arch: YoloV8Arch | None = None, calibrated: bool = True) -> dict[str, torch.Tensor]:
+def synthetic_state_dict(seed: int = 0, arch: YoloV8Arch | None = None, calibrated: bool = True,
+                         head_gain: float = 1.0) -> dict[str, torch.Tensor]:
     """Seeded random weights in the UNFUSED ultralytics layout (conv weight + BN statistics),
     rounded through fp16 like an ultralytics checkpoint.  Conv weights ~ N(0, 2.2/fan_in) keep the
     activations O(1) through all modules.  With ``calibrated`` the final 1x1 head convolutions are
@@ -53,6 +54,11 @@ def synthetic_state_dict(seed: int = 0, arch: YoloV8Arch | None = None, calibrat
                 sd[f"{s.name}.bias"] = torch.full((s.cout,), math.log(0.1 / 0.9) - 1.0)
             else:
                 sd[f"{s.name}.bias"] = 1.0 + 0.1 * rnd(s.cout)
+    if not calibrated and head_gain != 1.0:
+        # purely random heads answer with nearly constant class logits (std ~0.03 over an image); the gain spreads them
+        # so that a share of the anchors crosses conf 0.1 — a detector whose every decision is a near-tie (parity tests)
+        for lvl in range(3):
+            sd[f"model.22.cv3.{lvl}.2.weight"] = sd[f"model.22.cv3.{lvl}.2.weight"] * head_gain
     if calibrated and CALIB_PATH.exists():
         calib = json.loads(CALIB_PATH.read_text()).get(f"{arch.scale}-nc{arch.nc}-seed{seed}")
         if calib:

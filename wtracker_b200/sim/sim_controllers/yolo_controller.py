@@ -14,6 +14,9 @@ from wtracker_b200.sim.simulator import SimController, Simulator
 from wtracker_b200.utils.config_base import ConfigBase
 
 
+_PRED_KWARGS = {"imgsz", "conf", "iou", "max_det", "verbose", "device", "half"}   # what predict() honours or may ignore safely
+
+
 class B200Yolo:
     """What ``YoloConfig.load_model()`` returns: detector weights plus lazily built engines, one per
     (view size, imgsz, batch, thresholds).  Stands where ``ultralytics.YOLO`` stands in the reference."""
@@ -70,6 +73,7 @@ class YoloController(SimController):
         self.yolo_config = yolo_config
         self._camera_frames = deque(maxlen=timing_config.cycle_frame_num)
         self._model = yolo_config.load_model()
+        self._warned = False
 
     def on_sim_start(self, sim: Simulator):
         self._camera_frames.clear()
@@ -85,9 +89,22 @@ class YoloController(SimController):
         ``conf``; float32 if every frame has a box, float64 otherwise (yolo_controller.py:85-90)."""
         assert len(frames) > 0
         frames = list(frames)
-        if frames[0].ndim == 3:   # colour views: the detector consumes grey (the reference feeds 3 equal channels)
+        if frames[0].ndim == 3:
+            # The reference's experiments are grey (FrameReader defaults to IMREAD_GRAYSCALE and predict() replicates the
+            # channel, yolo_controller.py:68-69); the CUDA detector folds the three equal channels into layer 0.  A
+            # genuinely coloured view would need the 3-channel first layer: refuse it instead of silently using one channel.
+            for f in frames:
+                if not (np.array_equal(f[..., 0], f[..., 1]) and np.array_equal(f[..., 0], f[..., 2])):
+                    raise ValueError("wtracker_b200's detector takes grey views (three equal channels); got a colour frame")
             frames = [np.ascontiguousarray(f[..., 0]) for f in frames]
         kw = dict(self.yolo_config.pred_kwargs)
+        unsupported = sorted(set(kw) - _PRED_KWARGS)
+        if unsupported and not self._warned:
+            import warnings
+
+            warnings.warn(f"YoloController: pred_kwargs {unsupported} are not supported by the CUDA detector and are ignored "
+                          f"(supported: {sorted(_PRED_KWARGS)})", stacklevel=2)
+            self._warned = True
         eng = self._model.engine(frames[0].shape[:2], int(kw.get("imgsz", 384)), float(kw.get("conf", 0.1)),
                                  float(kw.get("iou", 0.7)), 1, max(len(frames), self.timing_config.cycle_frame_num))
         boxes, counts = eng.detect_views(frames)
