@@ -69,7 +69,7 @@ int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, int frame_w,
 /* K5  YOLOv8s backbone/neck/head as a program of fused ops over NHWC bf16 buffers            */
 /*   replaces ultralytics AutoBackend.forward (called from yolo_controller.py:72-78)           */
 /* ------------------------------------------------------------------------------------------ */
-enum { WT_OP_CONV0 = 0, WT_OP_CONV = 1, WT_OP_SPPF_POOL = 2, WT_OP_UPSAMPLE2X = 3 };
+enum { WT_OP_CONV0 = 0, WT_OP_CONV = 1, WT_OP_SPPF_POOL = 2 };
 enum { WT_ACT_NONE = 0, WT_ACT_SILU = 1 };
 enum { WT_DT_BF16 = 0, WT_DT_F32 = 1, WT_DT_U8 = 2 };
 
@@ -83,7 +83,7 @@ typedef struct wt_op {
     int32_t src, src_coff;       /* source buffer id, first channel                            */
     int32_t dst, dst_coff;       /* destination buffer id, first channel                       */
     int32_t res, res_coff;       /* residual buffer id (-1 = none), first channel              */
-    int32_t cin, cout;           /* conv channels (UPSAMPLE/POOL: cin = channels moved)        */
+    int32_t cin, cout;           /* conv channels (POOL: cin = channels pooled)                 */
     int32_t k, stride;           /* kernel size (1|3), stride (1|2); pad = k/2                 */
     int32_t act;                 /* WT_ACT_*                                                   */
     int64_t w_off, b_off;        /* byte offsets into the weight blob:                         */
@@ -322,7 +322,8 @@ int wt_precise_error(const uint8_t* frames, int n_frames, int frame_h, int frame
 /* test-only helpers (allocate + synchronise; never called by the product path)               */
 /* ------------------------------------------------------------------------------------------ */
 /* Runs one conv through the tcgen05 kernel and the scalar validation kernel on seeded data and
- * returns the max abs difference (bf16 outputs) in *max_abs_diff; prints one line when verbose. */
+ * returns the max abs difference (bf16 outputs) in *max_abs_diff; prints one line when verbose & 1; verbose & 2: the
+ * source slice is the whole source buffer (what the stride-2 pixel-pair kernel needs). */
 int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int k, int stride, int act,
                      int with_residual, int out_f32, int verbose, double* max_abs_diff);
 /* Chained form (wt_op.chain_w_off): conv (k, stride, SiLU) followed by a 1x1 conv cout -> cout (SiLU), once as ONE

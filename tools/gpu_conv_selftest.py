@@ -10,7 +10,7 @@ import subprocess
 import sys
 import time
 
-# cases run with WT_SELFTEST_TIGHT=1 (source slice == whole buffer): the stride-2 pixel-pair halo kernel
+# cases run with the source slice == whole buffer (verbose bit 1 of wt_selftest_conv): the stride-2 pixel-pair halo kernel
 TIGHT_CASES = [
     (2, 32, 32, 32, 64, 3, 2, 1, 0, 0),
     (3, 64, 48, 32, 64, 3, 2, 1, 0, 0),      # ragged rows: 24 output rows in 16-row tiles
@@ -105,7 +105,7 @@ import ctypes, sys
 from wtracker_b200._lib import lib
 args = [int(v) for v in sys.argv[1].split(',')]
 d = ctypes.c_double(-1.0)
-rc = lib().wt_selftest_conv(*args, 1, ctypes.byref(d))
+rc = lib().wt_selftest_conv(*args, 1 | (2 if len(sys.argv) > 2 and sys.argv[2] == 'tight' else 0), ctypes.byref(d))
 if rc != 0:
     print('ERROR', lib().wt_last_error().decode())
     sys.exit(2)
@@ -129,9 +129,9 @@ def main() -> int:
     for case in cases:
         arg = ",".join(str(v) for v in case)
         t0 = time.time()
-        env = dict(os.environ, WT_SELFTEST_TIGHT="1") if case in tight else None
+        extra = ["tight"] if case in tight else []
         try:
-            res = subprocess.run([sys.executable, "-c", SNIPPET, arg], capture_output=True, text=True, env=env, timeout=int(__import__("os").environ.get("WT_CASE_TIMEOUT", "40")))
+            res = subprocess.run([sys.executable, "-c", SNIPPET, arg, *extra], capture_output=True, text=True, timeout=int(__import__("os").environ.get("WT_CASE_TIMEOUT", "40")))
             status = {0: "OK", 2: "ERROR", 3: "MISMATCH"}.get(res.returncode, f"rc={res.returncode}")
             out = (res.stdout.strip() + " " + res.stderr.strip()[-400:]).strip()
         except subprocess.TimeoutExpired:

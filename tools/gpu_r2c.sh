@@ -1,6 +1,8 @@
 # Same-GPU A/B of conv variants at steady state (power-capped regime) + per-layer burst times.
 # Usage: bash tools/gpu_r2c.sh <tag> "<env assignments variant 1>" "<variant 2>" ...
+# Needs the tuning build (python -m wtracker_b200.build --tuning, done HERE before gpurun: it travels with the snapshot).
 export PYTHONPATH=$PWD
+export WTRACKER_B200_LIB=$PWD/wtracker_b200/_native/tuning/libwtracker_b200.so
 tag=$1; shift
 mkdir -p gpurun_out
 i=0

@@ -10,10 +10,13 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "_native" / "libwtracker_b200.so"
+import os
+
+# WTRACKER_B200_LIB points at another build of the same library (the tuning build of tools/gpu_r2c.sh)
+LIB_PATH = Path(os.environ.get("WTRACKER_B200_LIB") or Path(__file__).resolve().parent / "_native" / "libwtracker_b200.so")
 
 # ---- enums (mirror the header) --------------------------------------------------------------
-WT_OP_CONV0, WT_OP_CONV, WT_OP_SPPF_POOL, WT_OP_UPSAMPLE2X = 0, 1, 2, 3
+WT_OP_CONV0, WT_OP_CONV, WT_OP_SPPF_POOL = 0, 1, 2
 WT_ACT_NONE, WT_ACT_SILU = 0, 1
 WT_DT_BF16, WT_DT_F32, WT_DT_U8 = 0, 1, 2
 

@@ -59,16 +59,21 @@ def _newer(src: Path, obj: Path, deps: list[Path]) -> bool:
     return any(p.stat().st_mtime > t for p in [src, *deps])
 
 
-def build(verbose: bool = False, force: bool = False) -> Path:
+def build(verbose: bool = False, force: bool = False, tuning: bool = False) -> Path:
+    """``tuning``: a second library, ``_native/tuning/libwtracker_b200.so``, compiled with -DWT_TUNING_KNOBS so that the
+    WT_* environment variables select kernel variants (A/B runs: tools/gpu_r2c.sh points WTRACKER_B200_LIB at it).
+    The product library never reads the environment."""
     nvcc = find_nvcc()
-    OUT_DIR.mkdir(exist_ok=True)
+    out_dir = OUT_DIR / "tuning" if tuning else OUT_DIR
+    out_dir.mkdir(parents=True, exist_ok=True)
+    lib_path = out_dir / LIB_PATH.name
     headers = sorted(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "wtracker_b200.h"]
 
     def compile_one(name: str) -> Path:
         src = CSRC / name
-        obj = OUT_DIR / (src.stem + ".o")
+        obj = out_dir / (src.stem + ".o")
         if force or _newer(src, obj, headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [nvcc, *NVCC_FLAGS, *(["-DWT_TUNING_KNOBS"] if tuning else []), "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
@@ -82,14 +87,14 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as pool:
         objs = list(pool.map(compile_one, SOURCES))
 
-    if force or not LIB_PATH.exists() or any(o.stat().st_mtime > LIB_PATH.stat().st_mtime for o in objs):
-        cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcudart"]
+    if force or not lib_path.exists() or any(o.stat().st_mtime > lib_path.stat().st_mtime for o in objs):
+        cmd = [nvcc, "-shared", "-o", str(lib_path), *map(str, objs), "-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    path = build(verbose="-v" in sys.argv, force="-f" in sys.argv, tuning="--tuning" in sys.argv)
     print(path)

@@ -16,6 +16,13 @@ std::atomic<uint64_t> g_launch_count{0};
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 
+#ifdef WT_TUNING_KNOBS
+int knob(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+#endif
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -54,7 +61,7 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, void* bas
     else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
     // L2 promotion of TMA loads: 128 B by default; WT_TMAP_L2=256 | 64 | 0 for A/B runs
-    static const int l2_env = getenv("WT_TMAP_L2") ? atoi(getenv("WT_TMAP_L2")) : 128;
+    static const int l2_env = knob("WT_TMAP_L2", 128);
     const CUtensorMapL2promotion l2 = l2_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
                                       : l2_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                       : l2_env == 0  ? CU_TENSOR_MAP_L2_PROMOTION_NONE

@@ -43,6 +43,14 @@ extern std::atomic<uint64_t> g_launch_count;        // kernels launched by this 
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Tuning knobs: the product library never reads the environment — every knob IS its default.  A tuning build
+// (`python -m wtracker_b200.build --tuning`, -DWT_TUNING_KNOBS: tools/gpu_r2c.sh A/B runs only) reads WT_* variables.
+#ifdef WT_TUNING_KNOBS
+int knob(const char* name, int dflt);
+#else
+constexpr int knob(const char*, int dflt) { return dflt; }
+#endif
+
 // Opt-in for > 48 KB of dynamic shared memory.  Function attributes belong to the (device, context) pair, so the
 // "already raised to N bytes" state is kept PER DEVICE (one engine per GPU in one process is legal: DetectorEngine,
 // ResMLPEngine and HotPath all take a `device`), behind a mutex (launch paths are re-entrant per engine + stream).

@@ -51,7 +51,5 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
                  const TensorView& dst, int n_images, cudaStream_t stream);
 // SPPF: three chained 5x5/s1/p2 max-pools of src slice -> dst slices at dst.coff, +c, +2c
 int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream);
-// nearest 2x upsample of a channel slice into a slice of a (2h x 2w) buffer
-int upsample2x_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream);
 
 }  // namespace wt

@@ -36,8 +36,7 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kEpiGroups = 2;           // epilogue warp groups; group g drains TMEM accumulator g (tiles it % 2 == g)
 constexpr int kEpiThreads = 256;        // threads per epilogue group (8 warps = 4 TMEM lane quadrants x 2 column halves)
-constexpr int kMmaWarps = 2;            // MMA issuer warps; issuer w owns accumulator w (tiles it % 2 == w)
-constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+constexpr int kFirstEpiWarp = 3;        // warp 0 TMA producer, warp 1 MMA issuer, warp 2 spare (addend loader / second UMMA chain)
 constexpr int kThreads = kFirstEpiWarp * 32 + kEpiGroups * kEpiThreads;
 constexpr int kEpiBarrier = 1;          // named barrier ids kEpiBarrier + group
 constexpr int kStageBufBytes = 16384;   // one epilogue staging buffer: 128 rows x 128 B
@@ -93,10 +92,6 @@ struct ConvTcParams {
     // first layer on the tensor cores (conv0_tc_kernel): u8 grey input map [n][in_h][in_w]
     CUtensorMap tmIn;
     uint32_t mg_nb, mg_tx, mg_ty;   // multipliers for the tile-index divisions by n_blocks, tiles_x, tiles_y (fast_div)
-    // MMA issuer warps in use (1 | 2).  Two issuers take alternate tiles; that is only safe when every
-    // ring slot has ONE consumer (an mbarrier parity wait cannot tell phase k from phase k + 2), i.e. in
-    // the resident-weight halo kernel with one halo tile per output tile and an even number of halo stages.
-    int issuers;
     // halo kernel: pixel tiles per weight pass (NT template parameter).  A work item is a GROUP of nt tiles at the same
     // patch position of nt consecutive images; every weight tile streamed from L2 feeds the MMAs of all of them (the
     // 3x3 layers are bound by the L2 -> shared-memory fill, ~86 % of it weights: DESIGN.md), nt accumulators sit side
@@ -140,8 +135,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Work item t -> (N block, pixel patch origin).  CG == 2: a work item is a PAIR of x-adjacent patches, CTA
-// `rank` of the pair takes patch 2 * xb + rank (a patch beyond the map is all TMA zero-fill / clipped stores).
+// Work item t -> (N block, pixel patch origin).
 struct TileCoord {
     int nblk, x0, y0, n0;
 };
@@ -152,8 +146,7 @@ __device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
     if (magic) return int(__umulhi(uint32_t(n), magic));
     return d == 1 ? n : n / d;
 }
-template <int CG>
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, int rank) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t) {
     TileCoord c;
     int m = fast_div(t, p.n_blocks, p.mg_nb);
     c.nblk = t - m * p.n_blocks;
@@ -161,7 +154,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
     int xb = m - q * p.tiles_x;
     const int nb = fast_div(q, p.tiles_y, p.mg_ty);
     const int yb = q - nb * p.tiles_y;
-    if (CG == 2) xb = 2 * xb + rank;
     c.x0 = xb * p.tw;
     c.y0 = yb * p.th;
     c.n0 = nb * p.tn * p.nt;
@@ -179,10 +171,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int t, i
 
 // Fused class-logit head (wt_op.dot_off): thread (row, h) sums its half of the pixel's channels, the halves meet
 // in shared memory.
-template <int BN, int CG, int NT>
+template <int BN, int NT>
 __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                                   uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
-                                                  int warp, int lane, int rank) {
+                                                  int warp, int lane) {
     const int ew = warp - kFirstEpiWarp;
     const int g = ew >> 3, h = (ew >> 2) & 1;
     const int q = warp & 3;
@@ -191,10 +183,10 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
     const float* dw = sBias + p.cout;
     const int bar_id = kEpiBarrier + g;
     int it = g;
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const int first = blockIdx.x, step = gridDim.x;
     ptx::grid_dependency_wait();
     for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
-        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const TileCoord tc = decode_tile(p, tile);
         const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
@@ -213,8 +205,7 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);   // the leader's MMA thread waits for both CTAs
-                    else ptx::mbar_arrive(&tempty_bar[g]);
+                    ptx::mbar_arrive(&tempty_bar[g]);
                 }
             }
 #pragma unroll
@@ -258,10 +249,10 @@ __device__ __forceinline__ void conv_epilogue_dot(const ConvTcParams& p, uint8_t
 
 // CW = accumulator columns per thread and staging unit: 32 (bf16 output, units of 64 channels = 128-byte staging
 // rows) or 16 (f32 output: units of 32 channels = 128-byte rows; bf16 with BN == 32: one unit of 64-byte rows).
-template <int BN, int CG, int CW, int NT>
+template <int BN, int CW, int NT>
 __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                                  uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
-                                                 uint32_t tmem_base, int warp, int lane, int rank,
+                                                 uint32_t tmem_base, int warp, int lane,
                                                  const uint8_t* sAddAll, uint64_t* add_full, uint64_t* add_empty) {
     const int ew = warp - kFirstEpiWarp;
     const int g = ew >> 3;                  // epilogue group == accumulator buffer
@@ -280,10 +271,10 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
     const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
     uint32_t unit_counter = 0;
     int it = g;
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const int first = blockIdx.x, step = gridDim.x;
     ptx::grid_dependency_wait();   // residual loads and output stores come after the previous kernel
     for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
-        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const TileCoord tc = decode_tile(p, tile);
         const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
         const uint32_t aphase = (it >> 1) & 1;
         const float* bias = sBias + nblk * BN + h * CW;
@@ -331,8 +322,7 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2) ptx::mbar_arrive_leader(&tempty_bar[g]);
-                    else ptx::mbar_arrive(&tempty_bar[g]);
+                    ptx::mbar_arrive(&tempty_bar[g]);
                 }
             }
             float v[CW];
@@ -460,10 +450,10 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
 //   3. waits t2full[g], drains accumulator 2 + g with bias2 / act2 into the same staging buffers (the MMAs that
 //      read them have completed) and TMA-stores them.
 // cb = chain barriers: a2_full[2], t2full[2], t2empty[2].
-template <int BN, int CG>
+template <int BN>
 __device__ __forceinline__ void conv_epilogue_chain(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                                     uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* cb,
-                                                    uint32_t tmem_base, int warp, int lane, int rank) {
+                                                    uint32_t tmem_base, int warp, int lane) {
     constexpr int CW = 32;
     constexpr int kUnits = BN / 64;
     const int ew = warp - kFirstEpiWarp;
@@ -479,10 +469,10 @@ __device__ __forceinline__ void conv_epilogue_chain(const ConvTcParams& p, uint8
     const int bar_id = kEpiBarrier + g;
     const int xr = row & 7;
     int it = g;
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const int first = blockIdx.x, step = gridDim.x;
     ptx::grid_dependency_wait();
     for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
-        const TileCoord tc = decode_tile<CG>(p, tile, rank);
+        const TileCoord tc = decode_tile(p, tile);
         const uint32_t aphase = (it >> 1) & 1;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * CW;
 #pragma unroll 1
@@ -565,11 +555,11 @@ __device__ __forceinline__ void conv_epilogue_chain(const ConvTcParams& p, uint8
 
 // Second UMMA chain of the chained form, one elected lane of warp 2: A = the epilogue group's staging tiles,
 // B = W2 (resident, BN / 64 K blocks of [BN rows][128 B]), D = accumulator 2 + g.
-template <int BN, int CG>
+template <int BN>
 __device__ __forceinline__ void conv_chain_issuer(const ConvTcParams& p, const uint8_t* sStageAll, const uint8_t* sW2,
                                                   uint64_t* cb, uint64_t* w2_full, uint32_t tmem_base) {
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const int first = blockIdx.x, step = gridDim.x;
     const uint64_t b_desc0 = ptx::make_kmajor_desc<128>(ptx::smem_u32(sW2));
     const uint32_t b_hi = uint32_t(b_desc0 >> 32), b_lo0 = uint32_t(b_desc0);
     ptx::mbar_wait(w2_full, 0);
@@ -624,7 +614,7 @@ __device__ __forceinline__ void conv_epilogue_cat(const ConvTcParams& p, uint8_t
     const int first = blockIdx.x, step = gridDim.x;
     ptx::grid_dependency_wait();
     for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
-        const TileCoord tc = decode_tile<1>(p, tile, 0);
+        const TileCoord tc = decode_tile(p, tile);
         const uint32_t aphase = (it >> 1) & 1;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         // ---- pass 0: b = y1 + act(acc + bias), bf16, into the K = 32 staging tile
@@ -736,7 +726,7 @@ __device__ __forceinline__ void conv_cat_issuer(const ConvTcParams& p, const uin
     ptx::prefetch_tmap(&p.tmY);
     ptx::grid_dependency_wait();           // the cat buffer is written by earlier kernels
     if (first < p.num_tiles) {
-        const TileCoord tc = decode_tile<1>(p, first, 0);
+        const TileCoord tc = decode_tile(p, first);
         ptx::mbar_expect_tx(&yb[0], kStageBufBytes);
         ptx::tma_load_4d(const_cast<uint8_t*>(sY), &p.tmY, &yb[0], p.cat_coff, tc.x0, tc.y0, tc.n0);
     }
@@ -747,7 +737,7 @@ __device__ __forceinline__ void conv_cat_issuer(const ConvTcParams& p, const uin
         const uint32_t ph = (it >> 1) & 1;
         if (tile + step < p.num_tiles) {   // next tile's cat tile into the other buffer, once its previous user is done
             if (it >= 1) ptx::mbar_wait(&cb[2 + (g ^ 1)], ((it - 1) >> 1) & 1);   // t2full of tile it - 1
-            const TileCoord tn = decode_tile<1>(p, tile + step, 0);
+            const TileCoord tn = decode_tile(p, tile + step);
             ptx::mbar_expect_tx(&yb[g ^ 1], kStageBufBytes);
             ptx::tma_load_4d(const_cast<uint8_t*>(sY) + (g ^ 1) * kStageBufBytes, &p.tmY, &yb[g ^ 1], p.cat_coff, tn.x0,
                              tn.y0, tn.n0);
@@ -771,37 +761,35 @@ __device__ __forceinline__ void conv_cat_issuer(const ConvTcParams& p, const uin
     }
 }
 
-template <int BN, int CG, int NT = 1>
+template <int BN, int NT = 1>
 __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sStageAll, const float* sBias,
                                               uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* res_bar_all,
-                                              uint32_t tmem_base, int warp, int lane, int rank,
+                                              uint32_t tmem_base, int warp, int lane,
                                               const uint8_t* sAddAll = nullptr, uint64_t* add_full = nullptr,
                                               uint64_t* add_empty = nullptr, uint64_t* chain_bars = nullptr) {
     if (p.chain) {
-        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1)
-            conv_epilogue_chain<BN, CG>(p, sStageAll, sBias, tfull_bar, tempty_bar, chain_bars, tmem_base, warp, lane, rank);
+        if constexpr ((BN == 64 || BN == 128) && NT == 1)
+            conv_epilogue_chain<BN>(p, sStageAll, sBias, tfull_bar, tempty_bar, chain_bars, tmem_base, warp, lane);
         return;
     }
     if (p.dot_w) {
-        conv_epilogue_dot<BN, CG, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane, rank);
+        conv_epilogue_dot<BN, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, tmem_base, warp, lane);
         return;
     }
     if constexpr (BN >= 64) {
         if (!p.out_f32) {
-            conv_epilogue_cw<BN, CG, 32, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane,
-                                             rank, sAddAll, add_full, add_empty);
+            conv_epilogue_cw<BN, 32, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane, sAddAll, add_full, add_empty);
             return;
         }
     }
-    conv_epilogue_cw<BN, CG, 16, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane, rank,
+    conv_epilogue_cw<BN, 16, NT>(p, sStageAll, sBias, tfull_bar, tempty_bar, res_bar_all, tmem_base, warp, lane,
                                      sAddAll, add_full, add_empty);
 }
 
-template <int BN, int BK, int CG>
+template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-    using L = SmemLayout<BN / CG, BK>;   // a CTA of a pair holds half of the B tile (BN / 2 weight rows)
-    const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    using L = SmemLayout<BN, BK>;
+    const int first = blockIdx.x, step = gridDim.x;
     const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
     constexpr uint32_t kTmemCols = BN > 128 ? 512 : 2 * BN;   // double-buffered accumulator, a power of two >= 64
@@ -813,11 +801,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint8_t* smem = smem_raw;
     if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sA = smem;                                  // [stages][128][BK] bf16 (swizzled)
-    // 1x1 convs whose whole K extent of one N block fits (ConvTcParams.resident): B holds all cin_blocks K blocks of the
-    // CTA's N block, loaded once; the ring then carries A tiles only
-    const int kBSlots = p.resident ? p.cin_blocks : kStages;
-    uint8_t* sB = smem + kStages * L::kABytes;           // [stages | cin_blocks][BN][BK]  bf16 (swizzled)
-    uint8_t* sStage = sB + kBSlots * L::kBBytes;         // 2 groups x epi_bufs x 16 KB epilogue staging
+    uint8_t* sB = smem + kStages * L::kABytes;           // [stages][BN][BK]  bf16 (swizzled)
+    uint8_t* sStage = smem + kStages * L::kStageBytes;   // 2 groups x epi_bufs x 16 KB epilogue staging
     // addend patches [2 groups][BN / 32][32 px][128 B], 1024-byte aligned like everything before them (128-byte swizzle)
     const uint8_t* sAdd = sStage + kEpiGroups * p.epi_bufs * kStageBufBytes;
     float* sBias = reinterpret_cast<float*>(const_cast<uint8_t*>(sAdd) + (p.has_add ? add_smem_bytes(BN) : 0) +
@@ -851,7 +836,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 8 * CG);   // 8 epilogue warps per CTA of the pair
+            ptx::mbar_init(&tempty_bar[i], 8);   // the 8 warps of an epilogue group
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 2; ++i) {
@@ -863,13 +848,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        if (CG == 2) {
-            ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
-            ptx::tmem_relinquish_cg2();
-        } else {
-            ptx::tmem_alloc(tmem_slot, p.chain ? 4u * BN : kTmemCols);
-            ptx::tmem_relinquish();
-        }
+        ptx::tmem_alloc(tmem_slot, p.chain ? 4u * BN : kTmemCols);
+        ptx::tmem_relinquish();
     }
     // whole bias vector -> smem once per CTA
     {
@@ -884,7 +864,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
@@ -901,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             int it = 0;
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int g = it & 1;
-                const TileCoord tc = decode_tile<CG>(p, tile, rank);
+                const TileCoord tc = decode_tile(p, tile);
                 ptx::mbar_wait(&add_empty[g], ((it >> 1) & 1) ^ 1);
                 ptx::mbar_expect_tx(&add_full[g], BN * 128);
                 for (int sub = 0; sub < BN / 32; ++sub)
@@ -914,8 +893,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     if (warp == 2 && p.chain == 1) {
         // ------------------------------------------------------------------ second UMMA chain (chained 1x1 conv)
-        if constexpr ((BN == 64 || BN == 128) && CG == 1) {
-            if (ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+        if constexpr ((BN == 64 || BN == 128)) {
+            if (ptx::elect_one()) conv_chain_issuer<BN>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
         }
         __syncwarp();
     }
@@ -933,20 +912,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int kb = 0; kb < BN / 64; ++kb)
                 ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
         }
-        if (p.resident && first < p.num_tiles && ptx::elect_one()) {
-            // weights are constants: loaded before the grid dependency resolves.  Every tile of this CTA has the same N
-            // block (the host only sets `resident` when the tile stride is a multiple of n_blocks).
-            const int nblk0 = decode_tile<CG>(p, first, rank).nblk;
-            ptx::mbar_expect_tx(w2_full, p.cin_blocks * L::kBBytes);
-            for (int cb = 0; cb < p.cin_blocks; ++cb)
-                ptx::tma_load_2d(sB + cb * L::kBBytes, &p.tmB, w2_full, cb * BK, nblk0 * BN);
-        }
         __syncwarp();
         ptx::grid_dependency_wait();
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = first; tile < p.num_tiles; tile += step) {
-            const TileCoord tc = decode_tile<CG>(p, tile, rank);
+            const TileCoord tc = decode_tile(p, tile);
             const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
             for (int tap = 0; tap < taps; ++tap) {
                 const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
@@ -963,25 +934,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (ptx::elect_one()) {
-                        if (CG == 2) {
-                            // both CTAs' bytes are counted on the leader's barrier; each CTA loads its own pixel
-                            // patch and its half of the weight rows
-                            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-                            ptx::tma_load_4d_cg2(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
-                                                 p.src_coff + cb * BK, ax, ay, n0);
-                            ptx::tma_load_2d_cg2(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage],
-                                                 tap * p.cin + cb * BK, nblk * BN + rank * (BN / 2));
-                        } else if (p.resident) {
-                            ptx::mbar_expect_tx(&full_bar[stage], L::kABytes);
-                            ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
-                                             p.src_coff + cb * BK, ax, ay, n0);
-                        } else {
-                            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-                            ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
-                                             p.src_coff + cb * BK, ax, ay, n0);
-                            ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
-                                             nblk * BN);
-                        }
+                        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                        ptx::tma_load_4d(sA + stage * L::kABytes, &p.tmA[mapi], &full_bar[stage],
+                                         p.src_coff + cb * BK, ax, ay, n0);
+                        ptx::tma_load_2d(sB + stage * L::kBBytes, &p.tmB, &full_bar[stage], tap * p.cin + cb * BK,
+                                         nblk * BN);
                     }
                     __syncwarp();
                     if (++stage == kStages) {
@@ -992,31 +949,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
         }
     } else if (warp < kFirstEpiWarp) {
-        // ------------------------------------------------------------------ MMA issuers (warps 1, 2)
+        // ------------------------------------------------------------------ MMA issuer (warp 1; warp 2 idles here)
         // ONE elected lane per issuer warp runs the whole loop (waits included).  elect.sync tells the
         // compiler that a single thread is active, so descriptors and barrier addresses stay on the
         // uniform datapath; the descriptor low words advance by plain 32-bit adds (stage, K slice).
         // Issuer w handles tiles it = w, w + 2, ...; both walk the same smem ring, whose slot for the
         // g-th K block of the CTA is g % stages.
         const int w = warp - 1;
-        if (w < p.issuers && rank == 0 && ptx::elect_one()) {   // CTA pairs: only the leader issues
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM * CG, BN);
+        if (w == 0 && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
             const uint64_t a_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sA));
             const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
-            int it = w;
-            if (p.resident && first < p.num_tiles) {
-                ptx::mbar_wait(w2_full, 0);
-                ptx::tc_fence_after();
-            }
-            for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
+            int it = 0;
+            for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
                 const uint32_t g0 = uint32_t(it) * uint32_t(num_kb);
                 int stage = int(g0 % uint32_t(kStages));
                 uint32_t phase = (g0 / uint32_t(kStages)) & 1u;
-                uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = p.resident ? b_lo0 : b_lo0 + stage * (L::kBBytes >> 4);
+                uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -1025,42 +978,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         // advance 16 bf16 = 32 B along K inside the swizzle span: start address field += 2
-                        if (CG == 2)
-                            ptx::umma_bf16_lohi_cg2(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
-                                                    (kb | kk) != 0);
-                        else
-                            ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc, (kb | kk) != 0);
+                        ptx::umma_bf16_lohi(d_tmem, a_lo + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc, (kb | kk) != 0);
                     }
                     // frees the smem slot (in both CTAs of a pair) when these MMAs finish
-                    if (CG == 2) ptx::umma_commit_cg2(&empty_bar[stage]);
-                    else ptx::umma_commit(&empty_bar[stage]);
+                    ptx::umma_commit(&empty_bar[stage]);
                     a_lo += L::kABytes >> 4;
-                    b_lo += L::kBBytes >> 4;   // (resident: K block kb of the resident set; restarts with the next tile)
+                    b_lo += L::kBBytes >> 4;
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                         a_lo = a_lo0;
-                        if (!p.resident) b_lo = b_lo0;
+                        b_lo = b_lo0;
                     }
                 }
-                if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);   // accumulator complete (both CTAs' epilogues)
-                else ptx::umma_commit(&tfull_bar[ab]);
+                ptx::umma_commit(&tfull_bar[ab]);
             }
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
-        conv_epilogue<BN, CG>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, sAdd,
+        conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, sAdd,
                               add_full, add_empty, chain_bars);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();   // nobody signals a peer barrier or reads peer smem/TMEM after this
     if (warp == 1) {
         ptx::tc_fence_after();
-        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
-        else ptx::tmem_dealloc(tmem_base, p.chain ? 4u * BN : kTmemCols);
+        ptx::tmem_dealloc(tmem_base, p.chain ? 4u * BN : kTmemCols);
     }
 }
 
@@ -1100,26 +1045,25 @@ __host__ __device__ constexpr int halo_a_bytes(int bk, int s2, int il = 1) {
     return ((halo_rows(s2, il) * (s2 ? 128 : bk * 2) + 1023) / 1024) * 1024;
 }
 
-template <int BN, int BK, int CG, int S2, int IL = 1>
+template <int BN, int BK, int S2, int IL = 1>
 struct HaloSmem {
     static constexpr int kRowBytes = BK * 2;                 // weight rows: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
     static constexpr int kARowBytes = S2 ? 128 : BK * 2;     // halo rows (S2: a pixel pair)
     static constexpr int kABytes = halo_a_bytes(BK, S2, IL);
     static constexpr int kATxBytes = halo_rows(S2, IL) * kARowBytes;
-    static constexpr int kBBytes = (BN / CG) * kRowBytes;    // a CTA of a pair holds BN / 2 weight rows
+    static constexpr int kBBytes = (BN) * kRowBytes;    // a CTA of a pair holds BN / 2 weight rows
 };
 constexpr int kMaxAStages = 4;
 
-template <int BN, int BK, int CG, int S2, int NT, int IL>
+template <int BN, int BK, int S2, int NT, int IL>
 __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
-    static_assert(!S2 || (BK == 32 && CG == 1), "the stride-2 pair form is written for 32 input channels");
-    static_assert(IL == 1 || (IL == 2 && !S2 && CG == 1), "interleaved tiles: stride 1, single-CTA MMAs");
-    static_assert(NT == 1 || (CG == 1 && 2 * NT * BN <= 512), "tile groups: single-CTA MMAs, 2 x NT accumulators in TMEM");
-    using L = HaloSmem<BN, BK, CG, S2, IL>;
+    static_assert(!S2 || (BK == 32), "the stride-2 pair form is written for 32 input channels");
+    static_assert(IL == 1 || (IL == 2 && !S2), "interleaved tiles: stride 1, single-CTA MMAs");
+    static_assert(NT == 1 || (2 * NT * BN <= 512), "tile groups: single-CTA MMAs, 2 x NT accumulators in TMEM");
+    using L = HaloSmem<BN, BK, S2, IL>;
     constexpr int kARowBytes = L::kARowBytes;
     constexpr int kTapRowPitch = kHaloW * IL;        // pixels between vertically adjacent taps in the halo tile
-    const int rank = CG == 2 ? int(ptx::cluster_ctarank()) : 0;
-    const int first = blockIdx.x / CG, step = gridDim.x / CG;
+    const int first = blockIdx.x, step = gridDim.x;
     constexpr int kHaloABytes = L::kABytes;          // one halo tile
     constexpr int kAStageBytes = NT * kHaloABytes;   // one A stage = the halo tiles of a whole tile group
     constexpr int kRowBytes = L::kRowBytes;
@@ -1154,7 +1098,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint64_t* w2_full = res_bar + 10;
     uint64_t* y_full = res_bar + 11;      // [2] cat tile TMA -> epilogue group / second MMA chain (concat chain)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 13);
-    constexpr bool kCatCapable = (BN == 32 && BK == 32 && CG == 1 && S2 == 0 && NT == 1 && IL == 1);
+    constexpr bool kCatCapable = (BN == 32 && BK == 32 && S2 == 0 && NT == 1 && IL == 1);
 
     // shfl makes the warp index provably warp-uniform, so the role branches below are uniform branches
     // and the producer / MMA loops can live on the uniform datapath
@@ -1176,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 8 * CG);   // 8 epilogue warps per CTA of the pair
+            ptx::mbar_init(&tempty_bar[i], 8);   // the 8 warps of an epilogue group
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
@@ -1186,13 +1130,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        if (CG == 2) {
-            ptx::tmem_alloc_cg2(tmem_slot, kTmemCols);
-            ptx::tmem_relinquish_cg2();
-        } else {
-            ptx::tmem_alloc(tmem_slot, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
-            ptx::tmem_relinquish();
-        }
+        ptx::tmem_alloc(tmem_slot, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
+        ptx::tmem_relinquish();
     }
     // whole bias vector -> smem once per CTA
     {
@@ -1208,7 +1147,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
@@ -1218,8 +1156,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
     if (warp == 2 && p.chain) {
         // second UMMA chain of the chained 1x1 conv
-        if constexpr ((BN == 64 || BN == 128) && CG == 1 && NT == 1 && IL == 1) {
-            if (p.chain == 1 && ptx::elect_one()) conv_chain_issuer<BN, CG>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
+        if constexpr ((BN == 64 || BN == 128) && NT == 1 && IL == 1) {
+            if (p.chain == 1 && ptx::elect_one()) conv_chain_issuer<BN>(p, sStage, sW2, chain_bars, w2_full, tmem_base);
         }
         if constexpr (kCatCapable) {
             if (p.chain == 2 && ptx::elect_one())
@@ -1248,29 +1186,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         for (int tile = first; tile < p.num_tiles; tile += step) {
-            const TileCoord tc = decode_tile<CG>(p, tile, rank);
+            const TileCoord tc = decode_tile(p, tile);
             const int nblk = tc.nblk;
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 ptx::mbar_wait(&aempty[sa], pa ^ 1);
                 if (ptx::elect_one()) {
-                    if (CG == 2) {
-                        if (rank == 0) ptx::mbar_expect_tx(&afull[sa], 2 * L::kATxBytes);
-                        ptx::tma_load_4d_cg2(sA + sa * kAStageBytes, &p.tmA[0], &afull[sa], p.src_coff + cb * BK,
-                                             tc.x0 - 1, tc.y0 - 1, tc.n0);
-                    } else {
-                        ptx::mbar_expect_tx(&afull[sa], NT * L::kATxBytes);
+                    ptx::mbar_expect_tx(&afull[sa], NT * L::kATxBytes);
 #pragma unroll
-                        for (int sub = 0; sub < NT; ++sub) {   // the halo tiles of the group: same patch, images n0 .. n0 + NT - 1
-                            uint8_t* dst = sA + sa * kAStageBytes + sub * kHaloABytes;
-                            if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
-                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1, tc.n0 + sub);
-                            else if (IL == 2)   // (channel, x, image, row): two images per tile
-                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1,
-                                                 tc.n0 + 2 * sub, tc.y0 - 1);
-                            else
-                                ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1, tc.y0 - 1,
-                                                 tc.n0 + sub);
-                        }
+                    for (int sub = 0; sub < NT; ++sub) {   // the halo tiles of the group: same patch, images n0 .. n0 + NT - 1
+                        uint8_t* dst = sA + sa * kAStageBytes + sub * kHaloABytes;
+                        if (S2)   // pair view: x in pairs (pair ox0 - 1 first), y in input rows (row 2*oy0 - 1 first)
+                            ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], 0, tc.x0 - 1, 2 * tc.y0 - 1, tc.n0 + sub);
+                        else if (IL == 2)   // (channel, x, image, row): two images per tile
+                            ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1,
+                                             tc.n0 + 2 * sub, tc.y0 - 1);
+                        else
+                            ptx::tma_load_4d(dst, &p.tmA[0], &afull[sa], p.src_coff + cb * BK, tc.x0 - 1, tc.y0 - 1,
+                                             tc.n0 + sub);
                     }
                 }
                 __syncwarp();
@@ -1279,14 +1211,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 for (int tap = 0; tap < 9; ++tap) {
                     ptx::mbar_wait(&bempty[sb], pb ^ 1);
                     if (ptx::elect_one()) {
-                        if (CG == 2) {
-                            if (rank == 0) ptx::mbar_expect_tx(&bfull[sb], 2 * L::kBBytes);
-                            ptx::tma_load_3d_cg2(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap,
-                                                 nblk * BN + rank * (BN / 2));
-                        } else {
-                            ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
-                            ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap, nblk * BN);
-                        }
+                        ptx::mbar_expect_tx(&bfull[sb], L::kBBytes);
+                        ptx::tma_load_3d(sB + sb * L::kBBytes, &p.tmB, &bfull[sb], cb * BK, tap, nblk * BN);
                     }
                     __syncwarp();
                     if (++sb == kBStages) { sb = 0; pb ^= 1; }
@@ -1294,31 +1220,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             }
         }
     } else if (warp < kFirstEpiWarp) {
-        // MMA issuers (warps 1, 2): one elected lane each runs the whole loop for tiles it = w, w + 2, ...;
+        // MMA issuer (warp 1): one elected lane runs the whole loop;
         // descriptor low words advance by 32-bit adds (halo stage, weight stage, tap offset and K slice are all
         // additive in the start-address field).  Ring slots: halo tile g -> g % a_stages, weight tile g -> g % b_stages.
         const int w = warp - 1;
-        if (w < p.issuers && rank == 0 && ptx::elect_one()) {   // CTA pairs: only the leader issues
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM * CG, BN);
+        if (w == 0 && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN);
             const uint64_t a_desc0 = ptx::make_kmajor_desc_sbo<kARowBytes>(
                 ptx::smem_u32(sA), S2 ? 2 * kS2HaloW * 128 : kHaloW * kARowBytes);
             const uint64_t b_desc0 = ptx::make_kmajor_desc<kRowBytes>(ptx::smem_u32(sB));
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
-            int it = w;
+            int it = 0;
             if (kBStages == 9) {
                 // Weight ring of exactly nine slots (resident weights, or the host chose 9 stages): slot == tap, so
                 // every weight descriptor and barrier address in the unrolled tap loop is base + immediate and the
                 // ring bookkeeping disappears from the issue loop (the issuing thread, not the tensor pipe, bounds
                 // narrow-N layers).  Slot parity of channel block g of the CTA: g & 1.
-                for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
+                for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                     const int ab = it & 1;
                     const uint32_t d_tmem = tmem_base + ab * (NT * BN);
                     const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
                     int sa = int(ga % uint32_t(kAStages));
                     uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
                     uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4);
-                    const bool wait_b = !p.resident || it < p.issuers;
+                    const bool wait_b = !p.resident || it == 0;
                     ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         const uint32_t pb = (ga + cb) & 1u;
@@ -1339,29 +1265,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             for (int sub = 0; sub < NT; ++sub) {   // the same weight tile feeds every pixel tile of the group
 #pragma unroll
                                 for (int kk = 0; kk < BK / 16; ++kk) {
-                                    if (CG == 2)
-                                        ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_tap + 2 * kk, b_hi, idesc,
-                                                                (cb | tap | kk) != 0);
-                                    else
-                                        ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
+                                    ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
                                                             b_tap + 2 * kk, b_hi, idesc, (cb | tap | kk) != 0);
                                 }
                             }
                             if (!p.resident) {
-                                if (CG == 2) ptx::umma_commit_cg2(&bempty[tap]);
-                                else ptx::umma_commit(&bempty[tap]);
+                                ptx::umma_commit(&bempty[tap]);
                             }
                         }
-                        if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
-                        else ptx::umma_commit(&aempty[sa]);
+                        ptx::umma_commit(&aempty[sa]);
                         a_lo += kAStageBytes >> 4;
                         if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                     }
-                    if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
-                    else ptx::umma_commit(&tfull_bar[ab]);
+                    ptx::umma_commit(&tfull_bar[ab]);
                 }
             } else
-            for (int tile = first + w * step; tile < p.num_tiles; tile += p.issuers * step, it += p.issuers) {
+            for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * (NT * BN);
                 const uint32_t ga = uint32_t(it) * uint32_t(p.cin_blocks);
@@ -1375,8 +1294,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     pb = (gb / uint32_t(kBStages)) & 1u;
                 }
                 uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
-                // resident weights: both issuers wait once for all nine taps (phase 0 of each slot)
-                const bool wait_b = !p.resident || it < p.issuers;   // (resident: the first tile of each issuer)
+                // resident weights: waited for once, all nine taps (phase 0 of each slot)
+                const bool wait_b = !p.resident || it == 0;   // (resident: the first tile of each issuer)
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     ptx::mbar_wait(&afull[sa], pa);
@@ -1395,28 +1314,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         for (int sub = 0; sub < NT; ++sub) {
 #pragma unroll
                             for (int kk = 0; kk < BK / 16; ++kk) {
-                                if (CG == 2)
-                                    ptx::umma_bf16_lohi_cg2(d_tmem, a_tap + 2 * kk, a_hi, b_lo + 2 * kk, b_hi, idesc,
-                                                            (cb | tap | kk) != 0);
-                                else
-                                    ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
+                                ptx::umma_bf16_lohi(d_tmem + sub * BN, a_tap + sub * (kHaloABytes >> 4) + 2 * kk, a_hi,
                                                         b_lo + 2 * kk, b_hi, idesc, (cb | tap | kk) != 0);
                             }
                         }
                         if (!p.resident) {
-                            if (CG == 2) ptx::umma_commit_cg2(&bempty[sb]);
-                            else ptx::umma_commit(&bempty[sb]);
+                            ptx::umma_commit(&bempty[sb]);
                         }
                         b_lo += L::kBBytes >> 4;
                         if (++sb == kBStages) { sb = 0; pb ^= 1; b_lo = b_lo0; }
                     }
-                    if (CG == 2) ptx::umma_commit_cg2(&aempty[sa]);
-                    else ptx::umma_commit(&aempty[sa]);
+                    ptx::umma_commit(&aempty[sa]);
                     a_lo += kAStageBytes >> 4;
                     if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                 }
-                if (CG == 2) ptx::umma_commit_cg2(&tfull_bar[ab]);
-                else ptx::umma_commit(&tfull_bar[ab]);
+                ptx::umma_commit(&tfull_bar[ab]);
             }
         }
         __syncwarp();
@@ -1426,17 +1338,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 conv_epilogue_cat(p, sStage, sY, sBias, tfull_bar, tempty_bar, chain_bars, y_full, tmem_base, warp, lane);
         }
         if (p.chain != 2)
-            conv_epilogue<BN, CG, NT>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, rank, nullptr,
+            conv_epilogue<BN, NT>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, nullptr,
                                       nullptr, nullptr, chain_bars);
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (CG == 2) ptx::cluster_sync();   // nobody signals a peer barrier or reads peer smem/TMEM after this
     if (warp == 1) {
         ptx::tc_fence_after();
-        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
-        else ptx::tmem_dealloc(tmem_base, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
+        ptx::tmem_dealloc(tmem_base, p.chain == 2 ? 256u : (p.chain ? 4u * BN : kTmemCols));
     }
 }
 
@@ -1529,7 +1439,7 @@ __global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_co
         ptx::grid_dependency_wait();      // the input image is written by the crop / letterbox kernel
         int it = 0;
         for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
-            const TileCoord tc = decode_tile<1>(p, tile, 0);
+            const TileCoord tc = decode_tile(p, tile);
             const int s = it % kC0RawStages;
             ptx::mbar_wait(&raw_empty[s], ((it / kC0RawStages) & 1) ^ 1);
             if (ptx::elect_one()) {
@@ -1582,7 +1492,7 @@ __global__ void __launch_bounds__(kC0Threads, 1) conv0_tc_kernel(const __grid_co
         ptx::grid_dependency_wait();
         int it = g;
         for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
-            const TileCoord tc = decode_tile<1>(p, tile, 0);
+            const TileCoord tc = decode_tile(p, tile);
             // two staging tiles per group: the TMA store of the previous super-tile may still be reading the other one
             // (ncu: with one tile a quarter of the epilogue's samples sat at the barrier behind tma_store_wait_read<0>)
             uint8_t* stage = stage0 + ((it >> 1) & 1) * 2 * kStageBufBytes;
@@ -1702,7 +1612,6 @@ struct ConvTcPlan {
     int smem_bytes;
     bool halo;
     int bn, bk;
-    int cg;                    // CTAs per MMA (1, or 2 = cta_group::2 pairs launched as 2-CTA clusters)
     int s2;                    // halo kernel in its stride-2 pixel-pair form
     int nt = 1;                // halo kernel: pixel tiles per weight pass (ConvTcParams.nt)
     int il = 1;                // halo kernel: images interleaved per tile (ConvTcParams.il)
@@ -1739,7 +1648,7 @@ static int pick_bn(int cout, long long m_tiles, int sm_count, bool allow_192) {
         if (cout % bn != 0 || (bn == 192 && !allow_192)) continue;
         const long long tiles = m_tiles * (cout / bn);
         const long long waves = (tiles + sm_count - 1) / sm_count;
-        static const int fixed_env = getenv("WT_BN_FIXED") ? atoi(getenv("WT_BN_FIXED")) : 32;   // A/B knob
+        static const int fixed_env = knob("WT_BN_FIXED", 32);   // A/B knob
         const long long cost = waves * (bn + fixed_env);   // per-tile time ~ N plus a fixed part
         if (best == 0 || cost < best_cost) {
             best = bn;
@@ -1757,7 +1666,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     const int ho = d.dst.h, wo = d.dst.w;
     int sm_count = 148;
     wt_device_info(&sm_count, nullptr, nullptr);
-    static const int s2_env = getenv("WT_CONV_S2HALO") ? atoi(getenv("WT_CONV_S2HALO")) : 1;
+    static const int s2_env = knob("WT_CONV_S2HALO", 1);
     const bool tall_enough = ceil_div(ho, 16) * 16 * 4 <= ho * 5;
     // stride-2 pair form: 32 input channels that fill their buffer (a pixel pair is one contiguous 128-byte row)
     const bool halo_s2 = s2_env && d.k == 3 && d.stride == 2 && d.cin == 32 && d.src.ctot == 32 && d.src.coff == 0 &&
@@ -1820,16 +1729,12 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     ConvTcParams& p = pl->prm;
     pl->bn = bn;
     pl->bk = bk;
-    // CTA pairs (cta_group::2, M = 256, each CTA supplies half of the weight tile): implemented and parity-tested,
-    // but measured 15-30 % SLOWER than single-CTA MMAs on these layer shapes (B200, round 1), so off by default;
-    // WT_CONV_CG=2 selects it for N >= 128.
-    static const int cg_env = getenv("WT_CONV_CG") ? atoi(getenv("WT_CONV_CG")) : 1;
-    pl->cg = (cg_env == 2 && bn >= 128 && bk == 64 && !d.chain_w) ? 2 : 1;
+    // (CTA pairs — cta_group::2, M = 256 — were implemented in round 1, measured 15-30 % slower than single-CTA MMAs on
+    // these layer shapes and removed in round 2: git history has them.)
     pl->s2 = 0;
-    const int cg = pl->cg;
     // 3x3 / stride-1 layers use the halo-reuse kernel (tile = 16 rows x 8 columns of one image) unless the
     // map height wastes more than a quarter of the 16-row tiles (20x20 maps stay on the generic kernel)
-    static const int halo_env = getenv("WT_CONV_HALO") ? atoi(getenv("WT_CONV_HALO")) : 1;
+    static const int halo_env = knob("WT_CONV_HALO", 1);
     pl->halo = halo_env != 0 && halo_shape;
     if (pl->halo) {
         bk = d.cin % 64 == 0 ? 64 : 32;
@@ -1837,8 +1742,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         pl->s2 = halo_s2 ? 1 : 0;
         // 8 x 16 tiles of one image, or — where 16-row tiles would hang over the map (40 x 40) — 8 x 8 tiles of two
         // images interleaved row by row (WT_CONV_IL=0 switches the second form off for A/B runs)
-        static const int il_env = getenv("WT_CONV_IL") ? atoi(getenv("WT_CONV_IL")) : 1;
-        pl->il = (il_env && !halo_s2 && cg == 1 && !d.chain_w && bk == 64 && (bn == 64 || bn == 128 || bn == 192) &&
+        static const int il_env = knob("WT_CONV_IL", 1);
+        pl->il = (il_env && !halo_s2 && !d.chain_w && bk == 64 && (bn == 64 || bn == 128 || bn == 192) &&
                   ho % 16 != 0 && ho % 8 == 0) ? 2 : 1;
         p.tw = 8;
         p.th = 16 / pl->il;
@@ -1846,7 +1751,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     } else {
         choose_patch(wo, ho, d.batch, &p.tw, &p.th, &p.tn);
     }
-    p.tiles_x = ceil_div(ceil_div(wo, p.tw), cg);   // CTA pairs: pairs of x-adjacent patches
+    p.tiles_x = ceil_div(wo, p.tw);
     p.tiles_y = ceil_div(ho, p.th);
     p.tiles_n = ceil_div(d.batch, p.tn);
     p.n_blocks = d.cout / bn;
@@ -1858,7 +1763,7 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.src_coff = d.src.coff;
     p.dst_coff = d.dst.coff;
     p.res_coff = d.res.base ? d.res.coff : 0;
-    static const int silu_exact = getenv("WT_SILU_EXACT") ? atoi(getenv("WT_SILU_EXACT")) : 0;
+    static const int silu_exact = knob("WT_SILU_EXACT", 0);
     p.act = (d.act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : d.act;
     p.has_res = (d.res.base && !cat_chain) ? 1 : 0;   // concat chain: the residual is read from the cat tile in smem
     p.out_f32 = out_f32 ? 1 : 0;
@@ -1877,9 +1782,11 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     p.num_tiles = 0;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
     // shared-memory plan
-    p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
-    static const int epi_env = getenv("WT_EPI_BUFS") ? atoi(getenv("WT_EPI_BUFS")) : 0;   // A/B knob: 1 | 2 everywhere
-    if (epi_env == 1 || epi_env == 2) p.epi_bufs = epi_env;
+    // One staging buffer per epilogue group: the bytes buy more pipeline stages, which these latency-bound loops need more
+    // than a second staging buffer (round 2, same-GPU A/B at steady state: +0.5 % on the whole forward; the 1x1 layers
+    // at 40 x 40 / 20 x 20 gain 5-10 %).  WT_EPI_BUFS=2 (tuning builds) restores "two for 1x1 and narrow layers".
+    p.epi_bufs = 1;
+    if (knob("WT_EPI_BUFS", 1) == 2) p.epi_bufs = (d.k == 1 || bn <= 64) ? 2 : 1;
     if (d.chain_w) p.epi_bufs = bn / 64;   // the staging buffers of a group hold the whole bf16 tile (A of the second GEMM)
     if (cat_chain) p.epi_bufs = 2;         // b tile + output tile
     const int fixed = fixed_smem_bytes(p.epi_bufs) + (d.add.base ? add_smem_bytes(bn) : 0) +
@@ -1888,9 +1795,9 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         // Shared-memory plan of the halo kernel for `nt` pixel tiles per weight pass (one A stage = the halo tiles of a
         // whole group).  Returns false when fewer than two A stages (no load / MMA overlap) or two weight stages fit.
-        static const int nine_env = getenv("WT_CONV_NINE") ? atoi(getenv("WT_CONV_NINE")) : 1;
-        static const int resident_env = getenv("WT_CONV_RESIDENT") ? atoi(getenv("WT_CONV_RESIDENT")) : 1;
-        const int b_bytes = (bn / cg) * bk * 2;
+        static const int nine_env = knob("WT_CONV_NINE", 1);
+        static const int resident_env = knob("WT_CONV_RESIDENT", 1);
+        const int b_bytes = bn * bk * 2;
         auto plan = [&](int nt, int epi_bufs) -> bool {
             const int fx = fixed_smem_bytes(epi_bufs) + (cat_chain ? kCatSmemBytes : (d.chain_w ? bn * bn * 2 : 0));
             const int a_bytes = nt * halo_a_bytes(bk, pl->s2, pl->il);
@@ -1920,8 +1827,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         };
         // tile groups: as many pixel tiles per weight pass as TMEM (2 x nt x bn columns <= 512) and shared memory allow;
         // the chained forms keep one tile per pass (their second GEMM uses the other accumulators).  WT_CONV_NT caps it.
-        static const int nt_env = getenv("WT_CONV_NT") ? atoi(getenv("WT_CONV_NT")) : 4;
-        int nt_max = (cg == 1 && !d.chain_w) ? nt_env : 1;
+        static const int nt_env = knob("WT_CONV_NT", 4);
+        int nt_max = !d.chain_w ? nt_env : 1;
         if (nt_max != 1 && nt_max != 2 && nt_max != 4) nt_max = 1;
         // Among the feasible group sizes take the one with the fewest tile-times on this GPU: groups are dealt to the
         // SMs in waves, so a bigger group can cost a partly empty last wave (960 tiles on 148 SMs: 7 waves of single
@@ -1949,7 +1856,6 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
             }
         }
         if (ok) plan(best_nt, best_epi);
-        p.issuers = 1;
         if (!ok) {
             delete pl;
             set_error("not enough shared memory for the halo weight pipeline");
@@ -1962,29 +1868,10 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         p.il = 1;
         p.a_stages = 0;
         p.resident = 0;
-        p.issuers = 1;
-        const int stage_bytes = (kTileM + bn / cg) * bk * 2;
+        const int stage_bytes = (kTileM + bn) * bk * 2;
         p.stages = (kSmemBudget - fixed) / stage_bytes;
         if (p.stages > kMaxStages) p.stages = kMaxStages;
         pl->smem_bytes = p.stages * stage_bytes + fixed;
-        // 1x1 convs: the K extent of one N block resident in shared memory (loaded once per CTA instead of once per
-        // pixel tile; these layers are bound by the L2 -> shared-memory fill, two thirds of it weights) when at least four
-        // A stages still fit and every tile of a CTA has the same N block (148 SMs: n_blocks 1 | 2 | 4).
-        static const int res1_env = getenv("WT_CONV_RES1") ? atoi(getenv("WT_CONV_RES1")) : 1;
-        if (res1_env && d.k == 1 && cg == 1 && !d.chain_w && !d.dot_w && sm_count % p.n_blocks == 0) {
-            const int b_res = p.cin_blocks * bn * bk * 2, a_bytes = kTileM * bk * 2;
-            for (int epi = p.epi_bufs; epi >= 1; --epi) {
-                const int fx = fixed_smem_bytes(epi) + (d.add.base ? add_smem_bytes(bn) : 0);
-                const int a_stages = (kSmemBudget - fx - b_res) / a_bytes;
-                if (a_stages >= 4) {
-                    p.resident = 1;
-                    p.epi_bufs = epi;
-                    p.stages = a_stages > kMaxStages ? kMaxStages : a_stages;
-                    pl->smem_bytes = p.stages * a_bytes + b_res + fx;
-                    break;
-                }
-            }
-        }
     }
 
     const int sw_in = bk * 2;   // swizzle span == K-block row bytes
@@ -2028,14 +1915,14 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     if (pl->halo) {
         const uint64_t dims[3] = {uint64_t(d.cin), 9, uint64_t(d.cout)};
         const uint64_t str[2] = {uint64_t(d.cin) * 2, uint64_t(d.cin) * 2 * 9};
-        const uint32_t box[3] = {uint32_t(bk), 1, uint32_t(bn / cg)};
+        const uint32_t box[3] = {uint32_t(bk), 1, uint32_t(bn)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
     } else {
         const uint64_t ktot = uint64_t(d.k) * d.k * d.cin;
         const uint64_t dims[2] = {ktot, uint64_t(d.cout)};
         const uint64_t str[1] = {ktot * 2};
-        const uint32_t box[2] = {uint32_t(bk), uint32_t(bn / cg)};
+        const uint32_t box[2] = {uint32_t(bk), uint32_t(bn)};
         rc |= encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims, str, box,
                           sw_in);
     }
@@ -2065,8 +1952,8 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
     }
     p.tmP = p.tmA[0];
     if (d.add.base) {
-        if (pl->halo || pl->cg != 1 || p.tw < 2 || p.th < 2 || d.add.h * 2 != ho || d.add.w * 2 != wo) {
-            set_error("the upsampled addend needs the generic single-CTA kernel and an even pixel patch");
+        if (pl->halo || p.tw < 2 || p.th < 2 || d.add.h * 2 != ho || d.add.w * 2 != wo) {
+            set_error("the upsampled addend needs the generic kernel and an even pixel patch");
             rc = 1;
         } else {
             // f32 [n][h/2][w/2][ctot]; one box = 32 channels (128 B) of the (tw/2 x th/2 x tn) low-resolution patch
@@ -2126,19 +2013,18 @@ int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* 
     ConvTcPlan* pl = new ConvTcPlan();
     ConvTcParams& p = pl->prm;
     memset(&p, 0, sizeof(p));
-    pl->bn = 32; pl->bk = 32; pl->cg = 1; pl->s2 = 0; pl->halo = false;
+    pl->bn = 32; pl->bk = 32; pl->s2 = 0; pl->halo = false;
     pl->conv0 = true;
     const int ho = h / 2, wo = w / 2;
     p.tw = kC0TileW; p.th = kC0TileH; p.tn = 1;
     p.tiles_x = ceil_div(wo, p.tw); p.tiles_y = ceil_div(ho, p.th); p.tiles_n = batch;
     p.n_blocks = 1; p.ksize = 3; p.stride = 2; p.cin = 1; p.cin_blocks = 1; p.cout = 32;
     p.dst_coff = dst.coff;
-    static const int silu_exact = getenv("WT_SILU_EXACT") ? atoi(getenv("WT_SILU_EXACT")) : 0;
+    static const int silu_exact = knob("WT_SILU_EXACT", 0);
     p.act = (act == WT_ACT_SILU && !silu_exact) ? kActSiluTanh : act;
     p.bias = bias;
     p.out_w = wo; p.out_h = ho;
     p.epi_bufs = 2;
-    p.issuers = 1;
     p.nt = 1;
     p.il = 1;
     pl->pix_per_image_tiles = p.tiles_x * p.tiles_y;
@@ -2174,7 +2060,7 @@ int conv0_tc_plan_create(const uint8_t* src, int h, int w, const __nv_bfloat16* 
 }
 
 template <typename Kernel>
-static int launch_kernel(Kernel kernel, SmemOptIn* opt_in, const ConvTcParams& prm, int cg, int smem, int grid,
+static int launch_kernel(Kernel kernel, SmemOptIn* opt_in, const ConvTcParams& prm, int smem, int grid,
                          cudaStream_t stream) {
     WT_CHECK_CUDA(opt_in_smem(kernel, *opt_in, kSmemBudget));
     cudaLaunchConfig_t cfg = {};
@@ -2182,19 +2068,12 @@ static int launch_kernel(Kernel kernel, SmemOptIn* opt_in, const ConvTcParams& p
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     int na = 0;
-    static const int pdl_env = getenv("WT_CONV_PDL") ? atoi(getenv("WT_CONV_PDL")) : 1;
+    static const int pdl_env = knob("WT_CONV_PDL", 1);
     if (pdl_env) {   // start this kernel's prologue while the previous kernel of the stream drains
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
-        ++na;
-    }
-    if (cg > 1) {
-        attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = cg;
-        attr[na].val.clusterDim.y = 1;
-        attr[na].val.clusterDim.z = 1;
         ++na;
     }
     cfg.attrs = attr;
@@ -2204,22 +2083,22 @@ static int launch_kernel(Kernel kernel, SmemOptIn* opt_in, const ConvTcParams& p
     return 0;
 }
 
-template <int BN, int BK, int CG>
+template <int BN, int BK>
 static int launch_inst(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static SmemOptIn opt_in;
-    return launch_kernel(conv_tc_kernel<BN, BK, CG>, &opt_in, prm, CG, smem, grid, stream);
+    return launch_kernel(conv_tc_kernel<BN, BK>, &opt_in, prm, smem, grid, stream);
 }
 
-template <int BN, int BK, int CG, int S2 = 0, int NT = 1, int IL = 1>
+template <int BN, int BK, int S2 = 0, int NT = 1, int IL = 1>
 static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t stream) {
     static SmemOptIn opt_in;
-    return launch_kernel(conv_halo_kernel<BN, BK, CG, S2, NT, IL>, &opt_in, prm, CG, smem, grid, stream);
+    return launch_kernel(conv_halo_kernel<BN, BK, S2, NT, IL>, &opt_in, prm, smem, grid, stream);
 }
 
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
     ConvTcParams prm = pl->prm;
     const int tiles_n = ceil_div(n_images, prm.tn * prm.nt);   // (halo kernel: groups of nt images)
-    prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items (CTA pairs: per pair)
+    prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items
     prm.n_images = n_images;
     if (prm.num_tiles == 0) return 0;
     {
@@ -2232,9 +2111,7 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
         prm.mg_tx = magic(prm.tiles_x);
         prm.mg_ty = magic(prm.tiles_y);
     }
-    const int cg = pl->cg;
-    const int max_ctas = sm_count / cg * cg;
-    const int grid = prm.num_tiles * cg < max_ctas ? prm.num_tiles * cg : max_ctas;
+    const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;   // persistent: one CTA per SM
     const int smem = pl->smem_bytes;
     if (pl->conv0) {
         static SmemOptIn opt_in;
@@ -2257,64 +2134,60 @@ int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_
         const int nt = pl->nt;
         if (pl->s2) {         // 32 -> 32/64 channels, stride 2 (layer 1)
             switch (pl->bn * 10 + nt) {
-                case 641: return launch_halo<64, 32, 1, 1>(prm, smem, grid, stream);
-                case 321: return launch_halo<32, 32, 1, 1>(prm, smem, grid, stream);
-                case 642: return launch_halo<64, 32, 1, 1, 2>(prm, smem, grid, stream);
-                case 322: return launch_halo<32, 32, 1, 1, 2>(prm, smem, grid, stream);
+                case 641: return launch_halo<64, 32, 1>(prm, smem, grid, stream);
+                case 321: return launch_halo<32, 32, 1>(prm, smem, grid, stream);
+                case 642: return launch_halo<64, 32, 1, 2>(prm, smem, grid, stream);
+                case 322: return launch_halo<32, 32, 1, 2>(prm, smem, grid, stream);
             }
             set_error("no stride-2 halo instantiation for this (BN, NT)");
             return 1;
         }
         if (pl->bk == 32) {   // 32 input channels (the 160x160 C2f bottlenecks)
             switch (pl->bn * 10 + nt) {
-                case 641: return launch_halo<64, 32, 1>(prm, smem, grid, stream);
-                case 321: return launch_halo<32, 32, 1>(prm, smem, grid, stream);
-                case 642: return launch_halo<64, 32, 1, 0, 2>(prm, smem, grid, stream);
-                case 322: return launch_halo<32, 32, 1, 0, 2>(prm, smem, grid, stream);
-                case 644: return launch_halo<64, 32, 1, 0, 4>(prm, smem, grid, stream);
-                case 324: return launch_halo<32, 32, 1, 0, 4>(prm, smem, grid, stream);
+                case 641: return launch_halo<64, 32>(prm, smem, grid, stream);
+                case 321: return launch_halo<32, 32>(prm, smem, grid, stream);
+                case 642: return launch_halo<64, 32, 0, 2>(prm, smem, grid, stream);
+                case 322: return launch_halo<32, 32, 0, 2>(prm, smem, grid, stream);
+                case 644: return launch_halo<64, 32, 0, 4>(prm, smem, grid, stream);
+                case 324: return launch_halo<32, 32, 0, 4>(prm, smem, grid, stream);
             }
             set_error("no halo instantiation for this (BN, 32, NT)");
             return 1;
         }
-        if (pl->il == 1) switch ((pl->bn * 10 + cg) * 10 + nt) {
-            case 25621: return launch_halo<256, 64, 2>(prm, smem, grid, stream);
-            case 12821: return launch_halo<128, 64, 2>(prm, smem, grid, stream);
-            case 25611: return launch_halo<256, 64, 1>(prm, smem, grid, stream);
-            case 19211: return launch_halo<192, 64, 1>(prm, smem, grid, stream);
-            case 12811: return launch_halo<128, 64, 1>(prm, smem, grid, stream);
-            case 6411:  return launch_halo<64, 64, 1>(prm, smem, grid, stream);
-            case 3211:  return launch_halo<32, 64, 1>(prm, smem, grid, stream);
-            case 12812: return launch_halo<128, 64, 1, 0, 2>(prm, smem, grid, stream);
-            case 6412:  return launch_halo<64, 64, 1, 0, 2>(prm, smem, grid, stream);
-            case 3212:  return launch_halo<32, 64, 1, 0, 2>(prm, smem, grid, stream);
+        if (pl->il == 1) switch (pl->bn * 10 + nt) {
+            case 2561: return launch_halo<256, 64>(prm, smem, grid, stream);
+            case 1921: return launch_halo<192, 64>(prm, smem, grid, stream);
+            case 1281: return launch_halo<128, 64>(prm, smem, grid, stream);
+            case 641:  return launch_halo<64, 64>(prm, smem, grid, stream);
+            case 321:  return launch_halo<32, 64>(prm, smem, grid, stream);
+            case 1282: return launch_halo<128, 64, 0, 2>(prm, smem, grid, stream);
+            case 642:  return launch_halo<64, 64, 0, 2>(prm, smem, grid, stream);
+            case 322:  return launch_halo<32, 64, 0, 2>(prm, smem, grid, stream);
         }
-        if (pl->il == 2 && cg == 1) {   // two images per tile (40 x 40 maps)
+        if (pl->il == 2) {   // two images per tile (40 x 40 maps)
             switch (pl->bn * 10 + nt) {
-                case 1921: return launch_halo<192, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
-                case 1281: return launch_halo<128, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
-                case 641:  return launch_halo<64, 64, 1, 0, 1, 2>(prm, smem, grid, stream);
-                case 1282: return launch_halo<128, 64, 1, 0, 2, 2>(prm, smem, grid, stream);
-                case 642:  return launch_halo<64, 64, 1, 0, 2, 2>(prm, smem, grid, stream);
+                case 1921: return launch_halo<192, 64, 0, 1, 2>(prm, smem, grid, stream);
+                case 1281: return launch_halo<128, 64, 0, 1, 2>(prm, smem, grid, stream);
+                case 641:  return launch_halo<64, 64, 0, 1, 2>(prm, smem, grid, stream);
+                case 1282: return launch_halo<128, 64, 0, 2, 2>(prm, smem, grid, stream);
+                case 642:  return launch_halo<64, 64, 0, 2, 2>(prm, smem, grid, stream);
             }
         }
-        set_error("no halo instantiation for this (BN, CG, NT)");
+        set_error("no halo instantiation for this (BN, NT, IL)");
         return 1;
     }
-    switch ((pl->bn * 100 + pl->bk) * 10 + cg) {
-        case 256642: return launch_inst<256, 64, 2>(prm, smem, grid, stream);
-        case 128642: return launch_inst<128, 64, 2>(prm, smem, grid, stream);
-        case 256641: return launch_inst<256, 64, 1>(prm, smem, grid, stream);
-        case 192641: return launch_inst<192, 64, 1>(prm, smem, grid, stream);
-        case 128641: return launch_inst<128, 64, 1>(prm, smem, grid, stream);
-        case 64641:  return launch_inst<64, 64, 1>(prm, smem, grid, stream);
-        case 32641:  return launch_inst<32, 64, 1>(prm, smem, grid, stream);
-        case 256321: return launch_inst<256, 32, 1>(prm, smem, grid, stream);
-        case 128321: return launch_inst<128, 32, 1>(prm, smem, grid, stream);
-        case 64321:  return launch_inst<64, 32, 1>(prm, smem, grid, stream);
-        case 32321:  return launch_inst<32, 32, 1>(prm, smem, grid, stream);
+    switch (pl->bn * 100 + pl->bk) {
+        case 25664: return launch_inst<256, 64>(prm, smem, grid, stream);
+        case 19264: return launch_inst<192, 64>(prm, smem, grid, stream);
+        case 12864: return launch_inst<128, 64>(prm, smem, grid, stream);
+        case 6464:  return launch_inst<64, 64>(prm, smem, grid, stream);
+        case 3264:  return launch_inst<32, 64>(prm, smem, grid, stream);
+        case 25632: return launch_inst<256, 32>(prm, smem, grid, stream);
+        case 12832: return launch_inst<128, 32>(prm, smem, grid, stream);
+        case 6432:  return launch_inst<64, 32>(prm, smem, grid, stream);
+        case 3232:  return launch_inst<32, 32>(prm, smem, grid, stream);
         default:
-            set_error("no conv_tc instantiation for this (BN, BK, CG)");
+            set_error("no conv_tc instantiation for this (BN, BK)");
             return 1;
     }
 }

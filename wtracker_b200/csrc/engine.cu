@@ -12,7 +12,7 @@ namespace wt {
 static int64_t dtype_size(int dt) { return dt == WT_DT_F32 ? 4 : (dt == WT_DT_U8 ? 1 : 2); }
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static int64_t buf_align() {
-    static const int64_t a = getenv("WT_BUF_ALIGN") ? atoll(getenv("WT_BUF_ALIGN")) : 1024;
+    static const int64_t a = knob("WT_BUF_ALIGN", 1024);
     return a;
 }
 static int64_t buf_bytes(const wt_buf& b, int batch) {
@@ -94,13 +94,9 @@ void op_ranges(const wt_op& o, std::vector<ChanRange>& rd, std::vector<ChanRange
             rd.push_back({o.src, 0, 1});
             wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cout});
             break;
-        case WT_OP_SPPF_POOL:
+        default:   // WT_OP_SPPF_POOL
             rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
             wr.push_back({o.dst, o.dst_coff, o.dst_coff + 3 * o.cin});
-            break;
-        default:   // WT_OP_UPSAMPLE2X
-            rd.push_back({o.src, o.src_coff, o.src_coff + o.cin});
-            wr.push_back({o.dst, o.dst_coff, o.dst_coff + o.cin});
     }
 }
 bool overlap(const std::vector<ChanRange>& a, const std::vector<ChanRange>& b) {
@@ -220,7 +216,7 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
             if (o.w_off + int64_t(o.cout) * 9 * 4 > weight_bytes || o.b_off + int64_t(o.cout) * 4 > weight_bytes)
                 return fail("weight offsets out of range", i);
             // chain_w_off of a CONV0 op: the bf16 [32][32] hi | lo weight matrix of the tcgen05 form (-1: CUDA cores)
-            static const int c0tc_env = getenv("WT_CONV0_TC") ? atoi(getenv("WT_CONV0_TC")) : 1;
+            static const int c0tc_env = knob("WT_CONV0_TC", 1);
             if (o.chain_w_off >= 0 && conv_impl == 0 && c0tc_env && o.cout == 32 && e->bufs[o.src].w % 16 == 0) {
                 if (o.chain_w_off % 16 != 0 || o.chain_w_off + 2048 > weight_bytes) return fail("conv0 weight matrix out of range", i);
                 if (conv0_tc_plan_create(static_cast<const uint8_t*>(e->buf_ptr[o.src]), e->bufs[o.src].h, e->bufs[o.src].w,
@@ -231,12 +227,12 @@ extern "C" int wt_engine_create(const wt_buf* bufs, int n_bufs, const wt_op* ops
                     return fail(m.c_str(), i);
                 }
             }
-        } else if (o.kind != WT_OP_SPPF_POOL && o.kind != WT_OP_UPSAMPLE2X) {
+        } else if (o.kind != WT_OP_SPPF_POOL) {
             return fail("unknown op kind", i);
         }
     }
     // lanes: cross-lane hazards (read-after-write, write-after-write, write-after-read) -> event waits
-    static const int lanes_env = getenv("WT_LANES") ? atoi(getenv("WT_LANES")) : 1;
+    static const int lanes_env = knob("WT_LANES", 1);
     e->wait_on.assign(n_ops, -1);
     e->done_ev.assign(n_ops, nullptr);
     for (int i = 0; i < n_ops; ++i) {
@@ -312,9 +308,6 @@ extern "C" int wt_engine_forward(wt_engine* e, int n, int first_op, int last_op,
             case WT_OP_SPPF_POOL:
                 rc = sppf_pool_launch(view_of(e, o.src, o.src_coff), view_of(e, o.dst, o.dst_coff), o.cin, n, stream);
                 break;
-            case WT_OP_UPSAMPLE2X:
-                rc = upsample2x_launch(view_of(e, o.src, o.src_coff), view_of(e, o.dst, o.dst_coff), o.cin, n, stream);
-                break;
             default:
                 set_error("unknown op kind");
                 rc = 1;
@@ -364,8 +357,9 @@ extern "C" int wt_selftest_conv(int batch, int h, int w, int cin, int cout, int 
     if (wt_device_info(&sm, &cc, nullptr)) return 1;
     const int ho = h / stride, wo = w / stride;
     // source / destination sit inside wider buffers at a channel offset to exercise slicing
-    // (WT_SELFTEST_TIGHT=1: the source fills its buffer, which the stride-2 pixel-pair kernel requires)
-    const bool tight = getenv("WT_SELFTEST_TIGHT") && atoi(getenv("WT_SELFTEST_TIGHT"));
+    // (verbose bit 1: the source fills its buffer, which the stride-2 pixel-pair kernel requires)
+    const bool tight = (verbose & 2) != 0;
+    verbose &= 1;
     const int src_ct = tight ? cin : cin + 64, src_off = tight ? 0 : 32, dst_ct = cout + 64, dst_off = 32;
     const size_t n_src = size_t(batch) * h * w * src_ct, n_dst = size_t(batch) * ho * wo * dst_ct;
     const size_t n_w = size_t(cout) * k * k * cin;

@@ -248,119 +248,6 @@ __global__ void __launch_bounds__(kConv0Threads, MINB) conv0_kernel(const uint8_
     }
 }
 
-// Two-pixel form of the first layer: half the accumulators and inputs per thread (about 100 registers instead of
-// 167), so four CTAs instead of three fit an SM; the kernel is bound by dependent-issue latency, not by a pipe.
-template <int COUT>
-__global__ void __launch_bounds__(kConv0Threads, 4) conv0_px2_kernel(const uint8_t* __restrict__ src, int h, int w,
-                                                                     const float* __restrict__ w9,
-                                                                     const float* __restrict__ bias, int act,
-                                                                     __nv_bfloat16* __restrict__ dst, int dct, int dcoff,
-                                                                     long long total_threads) {
-    constexpr int G = COUT / 8;
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (idx >= total_threads) return;
-    const int g = int(idx % G);
-    long long q = idx / G;
-    const int ho = h / 2, wo = w / 2, pw = wo / 2;
-    const int strips = (ho + kConv0Rows - 1) / kConv0Rows;
-    const int xp = int(q % pw);
-    q /= pw;
-    const int ys = int(q % strips);
-    const int n = int(q / strips);
-    const int x0 = xp * 2;
-    const int y_begin = ys * kConv0Rows;
-    const int y_end = min(y_begin + kConv0Rows, ho);
-    const uint8_t* img = src + size_t(n) * h * w;
-
-    ptx::grid_launch_dependents();
-    const float ws = act == WT_ACT_SILU ? 0.5f : 1.0f;
-    uint64_t wreg[9][4], breg[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        breg[j] = ptx::pack_f32x2(ws * __ldg(bias + g * 8 + 2 * j), ws * __ldg(bias + g * 8 + 2 * j + 1));
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-            wreg[t][j] = ptx::pack_f32x2(ws * __ldg(w9 + (g * 8 + 2 * j) * 9 + t), ws * __ldg(w9 + (g * 8 + 2 * j + 1) * 9 + t));
-    }
-    ptx::grid_dependency_wait();
-    // one input row segment: columns 2*x0 .. 2*x0+3 (one aligned word) and column 2*x0-1
-    auto load_row = [&](int iy, int hh, uint32_t& v, uint32_t& left) {
-        v = 0u;
-        left = 0u;
-        if (iy >= 0 && iy < hh) {
-            const uint8_t* rowp = img + size_t(iy) * w + 2 * x0;
-            v = __ldg(reinterpret_cast<const uint32_t*>(rowp));
-            if (x0 > 0) left = __ldg(rowp - 1);
-        }
-    };
-    auto unpack = [&](uint32_t v, uint32_t left, float (&in)[5]) {
-        in[0] = byte_to_float<0>(left);
-        in[1] = byte_to_float<0>(v);
-        in[2] = byte_to_float<1>(v);
-        in[3] = byte_to_float<2>(v);
-        in[4] = byte_to_float<3>(v);
-    };
-    uint32_t v0, l0, v1, l1, v2, l2;
-    load_row(2 * y_begin - 1, h, v0, l0);
-    load_row(2 * y_begin, h, v1, l1);
-    load_row(2 * y_begin + 1, h, v2, l2);
-    float r0[5], r1[5], r2[5];
-    unpack(v0, l0, r0);
-    for (int y = y_begin; y < y_end; ++y) {
-        unpack(v1, l1, r1);
-        unpack(v2, l2, r2);
-        load_row(2 * y + 2, y + 1 < y_end ? h : 0, v1, l1);
-        load_row(2 * y + 3, y + 1 < y_end ? h : 0, v2, l2);
-        uint64_t acc[2][4];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[p][j] = breg[j];
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r0[2 * p + kw], wreg[kw][j]);
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r1[2 * p + kw], wreg[3 + kw][j]);
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-            for (int p = 0; p < 2; ++p)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ffma2_bcast(acc[p][j], r2[2 * p + kw], wreg[6 + kw][j]);
-        __nv_bfloat16* out = dst + ((size_t(n) * ho + y) * wo + x0) * dct + dcoff + g * 8;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float lo, hi;
-                ptx::unpack_f32x2(acc[p][j], lo, hi);
-                if (act == WT_ACT_SILU) {
-                    float tl, th;
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
-                    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
-                    uint64_t o;
-                    const uint64_t t2 = ptx::pack_f32x2(tl, th);
-                    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(o) : "l"(acc[p][j]), "l"(t2));
-                    ptx::unpack_f32x2(o, lo, hi);
-                }
-                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-                pk[j] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(out + size_t(p) * dct) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) r0[c] = r2[c];
-    }
-}
-
 // ------------------------------------------------------------------ SPPF pooling chain
 // One CTA per (image, 8-channel group): the 8 channels of a pixel are one 16-byte word, the slice
 // (h*w words) lives in shared memory, and each 5x5 max-pool is a horizontal then a vertical 5-tap max
@@ -478,25 +365,6 @@ __global__ void __launch_bounds__(kPoolThreads) sppf_pool_generic_kernel(const _
     }
 }
 
-// ------------------------------------------------------------------ nearest 2x upsample
-__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sct, int scoff,
-                                  __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c8, long long total) {
-    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    ptx::grid_launch_dependents();
-    ptx::grid_dependency_wait();
-    if (idx >= total) return;
-    const int g = int(idx % c8);
-    long long pix = idx / c8;
-    const int dw = 2 * sw, dh = 2 * sh;
-    const int x = int(pix % dw);
-    pix /= dw;
-    const int y = int(pix % dh);
-    const int n = int(pix / dh);
-    const uint4 v =
-        *reinterpret_cast<const uint4*>(src + ((size_t(n) * sh + (y >> 1)) * sw + (x >> 1)) * sct + scoff + g * 8);
-    *reinterpret_cast<uint4*>(dst + ((size_t(n) * dh + y) * dw + x) * dct + dcoff + g * 8) = v;
-}
-
 }  // namespace
 
 int conv_simt_launch(const ConvDesc& d, int n_images, cudaStream_t stream) {
@@ -536,20 +404,7 @@ int conv0_launch(const uint8_t* src, int h, int w, const float* w9, const float*
     const int threads = kConv0Threads;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dst.base);
-    // WT_CONV0_OCC=4 caps registers at 128 (4 CTAs / SM, a few spilled words) for A/B runs; default 3 CTAs / SM
-    static const int occ_env = getenv("WT_CONV0_OCC") ? atoi(getenv("WT_CONV0_OCC")) : 3;
-    auto* kernel = cout == 32 ? (occ_env == 4 ? conv0_kernel<32, 4> : conv0_kernel<32, 3>)
-                              : (cout == 16 ? conv0_kernel<16, 3> : conv0_kernel<64, 3>);
-    // WT_CONV0_PX=2: the two-pixel form (more resident warps) for A/B runs
-    static const int px_env = getenv("WT_CONV0_PX") ? atoi(getenv("WT_CONV0_PX")) : 4;
-    if (px_env == 2 && cout == 32) {
-        const long long total2 = (long long)n_images * strips * (w / 4) * (cout / 8);
-        const unsigned blocks2 = (unsigned)((total2 + threads - 1) / threads);
-        WT_CHECK_CUDA(launch_pdl(conv0_px2_kernel<32>, dim3(blocks2), dim3(threads), 0, stream, src, h, w, w9, bias, act, out,
-                                 dst.ctot, dst.coff, total2));
-        WT_LAUNCHED();
-        return 0;
-    }
+    auto* kernel = cout == 32 ? conv0_kernel<32, 3> : (cout == 16 ? conv0_kernel<16, 3> : conv0_kernel<64, 3>);
     WT_CHECK_CUDA(launch_pdl(kernel, dim3(blocks), dim3(threads), 0, stream, src, h, w, w9, bias, act, out, dst.ctot,
                              dst.coff, total));
     WT_LAUNCHED();
@@ -573,20 +428,6 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
     WT_CHECK_CUDA(launch_pdl(kernel, grid, dim3(kPoolThreads * G), smem, stream,
                              static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
                              static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w));
-    WT_LAUNCHED();
-    return 0;
-}
-
-int upsample2x_launch(const TensorView& src, const TensorView& dst, int c, int n_images, cudaStream_t stream) {
-    WT_REQUIRE(c % 8 == 0 && src.coff % 8 == 0 && dst.coff % 8 == 0 && src.ctot % 8 == 0 && dst.ctot % 8 == 0,
-               "upsample channel alignment");
-    WT_REQUIRE(dst.h == 2 * src.h && dst.w == 2 * src.w, "upsample doubles the spatial size");
-    const long long total = (long long)n_images * dst.h * dst.w * (c / 8);
-    if (total == 0) return 0;
-    const int threads = 256;
-    WT_CHECK_CUDA(launch_pdl(upsample2x_kernel, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, stream,
-                             static_cast<const __nv_bfloat16*>(src.base), src.h, src.w, src.ctot, src.coff,
-                             static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c / 8, total));
     WT_LAUNCHED();
     return 0;
 }
