@@ -176,7 +176,8 @@ typedef struct wt_post_params {
 
 /* out_boxes : f32 [n][max_det][6] = x1,y1,x2,y2 (original image px, clipped), conf, anchor index
  * out_count : i32 [n] kept boxes per image (0 => the reference returns a NaN row)
- * scratch   : >= wt_post_scratch_bytes(n, total_anchors) bytes                                  */
+ * scratch   : >= wt_post_scratch_bytes(n, total_anchors) bytes, 16-byte aligned, ZEROED once before its first use
+ *             (the max_det == 1 form keeps two words per image in it and leaves them zeroed after every call)    */
 int64_t wt_post_scratch_bytes(int n, int total_anchors);
 int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* p,
                   float* out_boxes, int32_t* out_count, void* scratch, void* stream);

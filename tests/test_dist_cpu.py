@@ -59,3 +59,41 @@ def test_gather_world_size_2():
     valid = (idx % 5 != 0)
     assert np.array_equal(full[:, 7] > 0, valid)
     assert np.allclose(full[valid, 0], idx[valid]) and np.isnan(full[~valid, :4]).all()
+
+
+def _worker_rows(rank, world, port, total, q):
+    """The offline driver's table: int32 rows (wt_result_rows layout, float columns bit-cast) through the same gather."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = frame_range(total, rank, world)
+    rows = np.zeros((hi - lo, 8), dtype=np.int32)
+    f = np.arange(lo, hi)
+    rows.view(np.float32)[:, 0] = f * 0.5
+    rows.view(np.float32)[:, 4] = np.where(f % 7 == 0, np.nan, 0.25)
+    rows[:, 5] = np.where(f % 7 == 0, -1, f * 3)
+    rows[:, 6] = f
+    rows[:, 7] = f % 7 != 0
+    full = gather_result_table(torch.from_numpy(rows), total)
+    if rank == 1:
+        q.put(full.numpy())
+    dist.destroy_process_group()
+
+
+def test_gather_int32_rows_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    total = 77                                   # odd: the shares differ by one row
+    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert full.dtype == np.int32 and full.shape == (total, 8)
+    f = np.arange(total)
+    assert np.array_equal(full[:, 6], f) and np.array_equal(full[:, 7], (f % 7 != 0).astype(np.int32))
+    assert np.array_equal(full.view(np.float32)[:, 0], (f * 0.5).astype(np.float32))
+    assert np.array_equal(np.isnan(full.view(np.float32)[:, 4]), f % 7 == 0)      # NaN bit patterns survive the gather
+    assert np.array_equal(full[:, 5], np.where(f % 7 == 0, -1, f * 3))

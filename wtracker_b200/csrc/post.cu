@@ -347,6 +347,92 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p) 
     if (tid == 0) p.out_count[img] = nk;
 }
 
+// max_det == 1 (the reference's setting, yolo_controller.py:72-78): the kept box is the arg-max of the confidence —
+// no key array, no sort, no suppression loop — so one image can be split over several CTAs.  CTA (split, img) scans its
+// share of the anchors and folds its best key (confidence bits << 32 | ~anchor: highest confidence, lowest index on
+// ties, exactly the order of the sort above) into best[img] with atomicMax; the CTA that arrives last at done[img]
+// decodes that one box and resets both words, so the scratch stays zeroed between calls.
+constexpr int kTop1Threads = 256;
+
+__global__ void __launch_bounds__(kTop1Threads) post_top1_kernel(const PostParams p, int splits, unsigned long long* best,
+                                                                 unsigned int* done) {
+    __shared__ unsigned long long s_red[kTop1Threads / 32];
+    __shared__ float s_lg[64];
+    __shared__ int s_last;
+    const int img = blockIdx.y, split = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = p.total_anchors;
+    const int per = (A + splits - 1) / splits;
+    const int a_lo = split * per, a_hi = min(A, a_lo + per);
+    constexpr int kUnroll = 8;
+    unsigned long long key = 0ull;
+    for (int a0 = a_lo + tid; a0 < a_hi; a0 += kUnroll * kTop1Threads) {
+        float lg[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {   // all loads in flight before the first use
+            const int a = a0 + u * kTop1Threads;
+            lg[u] = 0.f;
+            if (a < a_hi) {
+                const int l = level_of(p, a);
+                const wt_head_level& L = p.lv[l];
+                lg[u] = L.cls_logit ? __ldg(L.cls_logit + size_t(img) * L.h * L.w + (a - p.level_start[l]))
+                                    : p.sc_logit[size_t(img) * A + a];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int a = a0 + u * kTop1Threads;
+            const float conf = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-lg[u])));
+            if (a < a_hi && conf > p.pp.conf_thres) {
+                const unsigned long long k = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - unsigned(a));
+                key = k > key ? k : key;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane == 0) s_red[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kTop1Threads / 32; ++w) key = s_red[w] > key ? s_red[w] : key;
+        if (key) atomicMax(best + img, key);
+        __threadfence();
+        s_last = atomicAdd(done + img, 1u) == unsigned(splits - 1);
+    }
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+    __threadfence();
+    unsigned long long k = 0ull;
+    if (lane == 0) {
+        k = atomicExch(best + img, 0ull);
+        done[img] = 0u;
+    }
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k == 0ull) {
+        if (lane == 0) p.out_count[img] = 0;
+        return;
+    }
+    const int a = int(0xFFFFFFFFu - unsigned(k & 0xFFFFFFFFull));
+    float b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.box_from_feat) decode_box_from_feat(p, img, a, s_lg, lane, b);
+    else if (lane == 0) decode_box(p, img, a, b);
+    if (lane == 0) {
+        float x1 = __fdiv_rn(__fsub_rn(b[0], p.pp.pad_x), p.pp.gain), y1 = __fdiv_rn(__fsub_rn(b[1], p.pp.pad_y), p.pp.gain);
+        float x2 = __fdiv_rn(__fsub_rn(b[2], p.pp.pad_x), p.pp.gain), y2 = __fdiv_rn(__fsub_rn(b[3], p.pp.pad_y), p.pp.gain);
+        const float W = float(p.pp.img_w), H = float(p.pp.img_h);
+        x1 = fminf(fmaxf(x1, 0.f), W); x2 = fminf(fmaxf(x2, 0.f), W);
+        y1 = fminf(fmaxf(y1, 0.f), H); y2 = fminf(fmaxf(y2, 0.f), H);
+        float* o = p.out_boxes + size_t(img) * 6;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        o[4] = __uint_as_float(unsigned(k >> 32));
+        o[5] = float(a);
+        p.out_count[img] = 1;
+    }
+}
+
 __global__ void track_rows_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ count, int max_det,
                                   const int32_t* __restrict__ crop_x, const int32_t* __restrict__ crop_y, int cam_w,
                                   int cam_h, int mic_w, int mic_h, double* __restrict__ worm, double* __restrict__ mic,
@@ -390,7 +476,8 @@ extern "C" int wt_track_rows(const float* boxes, const int32_t* count, int max_d
 }
 
 extern "C" int64_t wt_post_scratch_bytes(int n, int total_anchors) {
-    return int64_t(n) * total_anchors * (4 * 4 + 4 + 4 + 4) + 256;
+    // candidate boxes / confidences / indices / logits, then (16-byte aligned) best[n] u64 + done[n] u32 of the arg-max form
+    return ((int64_t(n) * total_anchors * (4 * 4 + 4 + 4 + 4) + 15) / 16) * 16 + int64_t(n) * 12 + 256;
 }
 
 extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, const wt_post_params* pp,
@@ -440,6 +527,18 @@ extern "C" int wt_decode_nms(const wt_head_level* levels, int n_levels, int n, c
         const long long threads = (long long)n * total * 16;
         cls_logit_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n);
         WT_LAUNCHED();
+    }
+    if (pp->max_det == 1) {
+        // arg-max form: enough CTAs per image to fill the GPU twice over (n = 64 -> 5 per image, n = 1 -> 16)
+        int sm_count = 148;
+        wt_device_info(&sm_count, nullptr, nullptr);
+        int splits = (2 * sm_count + n - 1) / n;
+        splits = splits < 1 ? 1 : (splits > 16 ? 16 : splits);
+        uint8_t* tail = sc + ((size_t(n) * total * 28 + 15) / 16) * 16;
+        post_top1_kernel<<<dim3(splits, n), kTop1Threads, 0, static_cast<cudaStream_t>(stream)>>>(
+            p, splits, reinterpret_cast<unsigned long long*>(tail), reinterpret_cast<unsigned int*>(tail + size_t(n) * 8));
+        WT_LAUNCHED();
+        return 0;
     }
     post_kernel<<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     WT_LAUNCHED();
