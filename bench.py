@@ -546,6 +546,7 @@ def run_b200(args, rank: int, world: int, local_rank: int) -> dict | None:
                                    torch.cuda.current_stream().cuda_stream), "wt_result_rows")
     g0 = torch.cuda.Event(enable_timing=True)
     g1 = torch.cuda.Event(enable_timing=True)
+    gather_result_table(torch.zeros_like(table), world * n_local)   # untimed: NCCL sets up channels / buffers for this size once
     barrier()
     g0.record()
     full_table = gather_result_table(table, world * n_local)     # NCCL all_gather when world > 1
@@ -746,6 +747,11 @@ def run_offline_workload(args, rank: int, world: int, local_rank: int) -> dict |
     eng = DetectorEngine(synthetic_state_dict(args.seed), (VIEW, VIEW), IMGSZ, batch=args.batch, max_det=1, device=str(dev))
     sched = lambda first, n: crop_schedule(track, first, n)
     run_offline(eng, frames, sched, min(args.frames, 64 * args.batch * world), rank, world)     # warm-up incl. communicator
+    if world > 1:       # NCCL sets up its channels / buffers for the real table size once, outside the timed job
+        from wtracker_b200.sharding import frame_range, gather_result_table
+
+        lo, hi = frame_range(args.frames, rank, world)
+        gather_result_table(torch.zeros((hi - lo, 8), dtype=torch.int32, device=dev), args.frames)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
