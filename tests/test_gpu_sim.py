@@ -90,7 +90,7 @@ def test_closed_loop_yolo_controller_matches_oracle_loop():
     (CSV / MLP traces above); the detection floats differ from the fp32 oracle by < 0.5 px, which can
     flip round() at a .5 boundary, so movement vectors may differ by one pixel — and because every
     cycle re-centres on the worm the difference must not accumulate."""
-    n = 9 * 8
+    n = 9 * 30
     frames, track = synth.make_frames(n, seed=3, border_visit=False)
     init = (int(track[0, 0]), int(track[0, 1]))
     exp, t = make_timing(n, init=init)
@@ -99,10 +99,54 @@ def test_closed_loop_yolo_controller_matches_oracle_loop():
     Simulator(t, exp, a, reader=reader).run()
     b = Recorder(OracleYoloController(t, 384))
     Simulator(t, exp, b, reader=ArrayReader(frames)).run()
-    assert len(a.vec) == len(b.vec) == 8
+    assert len(a.vec) == len(b.vec) == 30
     dv = np.abs(np.array(a.vec) - np.array(b.vec))
     dp = np.abs(np.array(a.pos) - np.array(b.pos))
     assert dv.max() <= 1 and dp.max() <= 2, (a.vec, b.vec)
     assert (dv == 0).all(axis=1).mean() >= 0.5
     # and it does track: the platform ends within a few pixels of the worm head
     assert np.abs(np.array(a.pos[-1]) - track[-1, :2]).max() < 15
+
+
+def test_lazy_views_equal_buffered_views():
+    """The controller buffers (frame, origin) descriptors and lets the GPU cut the views (frame ingest); with
+    ``lazy_views=False`` it buffers cropped views like the reference.  Both must give the same loop, and a descriptor
+    must materialise to exactly the view the reference would have buffered — also where the view hangs over the border."""
+    from wtracker_b200.sim.sim_controllers.yolo_controller import LazyView
+
+    n = 9 * 6
+    frames, track = synth.make_frames(n, seed=5, border_visit=False)
+    init = (int(track[0, 0]), int(track[0, 1]))
+    exp, t = make_timing(n, init=init)
+    runs = []
+    for lazy in (True, False):
+        rec = Recorder(YoloController(t, YoloConfig("synthetic:0"), lazy_views=lazy))
+        Simulator(t, exp, rec, reader=ArrayReader(frames)).run()
+        runs.append(rec)
+    assert runs[0].vec == runs[1].vec and runs[0].pos == runs[1].pos and len(runs[0].vec) == 6
+    for origin in ((-40, 500), (1700, -25), (800, 900), (300, 200)):
+        lv = LazyView(frames[3], origin[0], origin[1], 360, 360)
+        want = synth.camera_view(frames[3], (origin[0] + 180, origin[1] + 180), 360)
+        assert np.array_equal(np.asarray(lv), want) and lv.shape == (360, 360)
+
+
+def test_cycle_predict_all_matches_oracle():
+    """``_cycle_predict_all`` (what LoggingController logs, yolo_controller.py:108-109): all N buffered views of a cycle in
+    one detector pass, against the fp32 oracle on the same views."""
+    n = 9 * 2
+    frames, track = synth.make_frames(n, seed=7, border_visit=False)
+    exp, t = make_timing(n, init=(int(track[0, 0]), int(track[0, 1])))
+
+    class Grab(YoloController):
+        def on_cycle_end(self, sim):
+            self.got = self._cycle_predict_all(sim)
+            self.views = [np.asarray(v) for v in self._camera_frames]
+            super().on_cycle_end(sim)
+
+    ctrl = Grab(t, YoloConfig("synthetic:0"))
+    Simulator(t, exp, ctrl, reader=ArrayReader(frames)).run()
+    assert ctrl.got.shape == (9, 4) and len(ctrl.views) == 9
+    ref = Y.YoloOracle(oracle_model(), 384, max_det=1).predict(ctrl.views)
+    assert ref.dtype == ctrl.got.dtype
+    assert np.allclose(ctrl.got, ref, atol=0.5, equal_nan=True), np.nanmax(np.abs(ctrl.got - ref))
+    assert np.isfinite(ctrl.got).all()

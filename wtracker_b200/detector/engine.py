@@ -174,6 +174,48 @@ class DetectorEngine:
             self._h_boxes = self._h_out[: self.batch * self.max_det * 6].view(torch.float32).view(self.batch, self.max_det, 6).numpy()
             self._h_count = self._h_out[self.batch * self.max_det * 6:].numpy()
 
+    def detect_frames(self, frames: list[np.ndarray], crop_x: list[int], crop_y: list[int]) -> tuple[np.ndarray, np.ndarray]:
+        """Host path with the crop on the device (frame ingest: reference utils/frame_reader.py:137-144 +
+        view_controller.py:45-61): ``frames`` are whole (H, W) u8 grey frames, ``crop_x / crop_y`` the camera-view
+        origins in frame coordinates (may hang over the border: replicate).  The frames go through a persistent pinned
+        buffer to the device in ONE copy per chunk, the crop kernel cuts the views there.  Same return as
+        ``detect_views``."""
+        n = len(frames)
+        fh, fw = frames[0].shape
+        boxes = np.zeros((n, self.max_det, 6), np.float32)
+        counts = np.zeros((n,), np.int32)
+        with torch.cuda.device(self.device):
+            self._host_staging()
+            if getattr(self, "_frame_shape", None) != (fh, fw):
+                self._frame_shape = (fh, fw)
+                self._h_frames = torch.empty((self.batch, fh, fw), dtype=torch.uint8).pin_memory()
+                self._h_frames_np = self._h_frames.numpy()
+                self._d_frames = torch.empty((self.batch, fh, fw), dtype=torch.uint8, device=self.device)
+                self._h_desc = torch.zeros((2, self.batch), dtype=torch.int32).pin_memory()
+                self._d_desc = torch.zeros((2, self.batch), dtype=torch.int32, device=self.device)
+            stream = torch.cuda.current_stream()
+            own = self.out_boxes.data_ptr() == self._out_words.data_ptr()
+            for s in range(0, n, self.batch):
+                m = min(self.batch, n - s)
+                hd = self._h_desc.numpy()
+                for i in range(m):
+                    f = frames[s + i]
+                    assert f.shape == (fh, fw) and f.dtype == np.uint8, "frames must be grey u8 of one size"
+                    np.copyto(self._h_frames_np[i], f)
+                    hd[0, i], hd[1, i] = crop_x[s + i], crop_y[s + i]
+                self._d_frames[:m].copy_(self._h_frames[:m], non_blocking=True)
+                self._d_desc.copy_(self._h_desc, non_blocking=True)
+                b, c = self.detect_crops(self._d_frames, self._iota[:m], self._d_desc[0, :m], self._d_desc[1, :m])
+                if own:
+                    self._h_out.copy_(self._out_words, non_blocking=True)
+                    stream.synchronize()
+                    boxes[s: s + m] = self._h_boxes[:m]
+                    counts[s: s + m] = self._h_count[:m]
+                else:
+                    boxes[s: s + m] = b.cpu().numpy()
+                    counts[s: s + m] = c.cpu().numpy()
+        return boxes, counts
+
     def detect_views(self, views: list[np.ndarray]) -> tuple[np.ndarray, np.ndarray]:
         """Host path (what ``YoloController.predict`` calls): list of (h, w) u8 grey camera views -> (boxes
         [n, max_det, 6], count [n]) numpy.  Per chunk of ``batch`` views: the views are written straight into a

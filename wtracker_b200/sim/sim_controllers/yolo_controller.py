@@ -67,19 +67,49 @@ class YoloConfig(ConfigBase):
         return self.model
 
 
+class LazyView:
+    """A camera view that has not been cut out yet: the whole grey frame (a reference, no copy) and the view's origin in
+    frame coordinates.  The reference's controller buffers one cropped view per frame (yolo_controller.py:58-59) although
+    it detects on one in ``cycle_frame_num`` of them; here the buffer holds descriptors, and the frames that ARE detected
+    travel whole to the GPU where the crop kernel cuts the views (replicate borders included).  ``np.asarray(view)``
+    still gives the pixels the reference would have buffered."""
+
+    __slots__ = ("frame", "x0", "y0", "w", "h")
+
+    def __init__(self, frame: np.ndarray, x0: int, y0: int, w: int, h: int):
+        self.frame, self.x0, self.y0, self.w, self.h = frame, int(x0), int(y0), int(w), int(h)
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self.w, self.h      # rows x columns exactly as ViewController._custom_view slices them (w/h swapped, square views)
+
+    def __array__(self, dtype=None, copy=None):
+        f = self.frame
+        rows = np.clip(np.arange(self.y0, self.y0 + self.w), 0, f.shape[0] - 1)
+        cols = np.clip(np.arange(self.x0, self.x0 + self.h), 0, f.shape[1] - 1)
+        out = f[np.ix_(rows, cols)]
+        return out if dtype is None else out.astype(dtype)
+
+
 class YoloController(SimController):
-    def __init__(self, timing_config, yolo_config: YoloConfig):
+    def __init__(self, timing_config, yolo_config: YoloConfig, lazy_views: bool = True):
         super().__init__(timing_config)
         self.yolo_config = yolo_config
         self._camera_frames = deque(maxlen=timing_config.cycle_frame_num)
         self._model = yolo_config.load_model()
         self._warned = False
+        self.lazy_views = lazy_views     # False: buffer cropped views like the reference does
 
     def on_sim_start(self, sim: Simulator):
         self._camera_frames.clear()
 
     def on_camera_frame(self, sim: Simulator):
-        self._camera_frames.append(sim.camera_view())
+        frame = sim.view.current_frame() if self.lazy_views else None
+        if frame is not None and frame.ndim == 2 and sim.view.camera_size[0] == sim.view.camera_size[1]:
+            x0, y0, w, h = sim.view.camera_position
+            self._camera_frames.append(LazyView(frame, x0, y0, w, h))
+        else:
+            self._camera_frames.append(sim.camera_view())
 
     def on_cycle_end(self, sim: Simulator):
         self._camera_frames.clear()
@@ -89,7 +119,10 @@ class YoloController(SimController):
         ``conf``; float32 if every frame has a box, float64 otherwise (yolo_controller.py:85-90)."""
         assert len(frames) > 0
         frames = list(frames)
-        if frames[0].ndim == 3:
+        lazy = all(isinstance(f, LazyView) for f in frames)
+        if not lazy:
+            frames = [np.asarray(f) if isinstance(f, LazyView) else f for f in frames]
+        if not lazy and frames[0].ndim == 3:
             # The reference's experiments are grey (FrameReader defaults to IMREAD_GRAYSCALE and predict() replicates the
             # channel, yolo_controller.py:68-69); the CUDA detector folds the three equal channels into layer 0.  A
             # genuinely coloured view would need the 3-channel first layer: refuse it instead of silently using one channel.
@@ -107,7 +140,10 @@ class YoloController(SimController):
             self._warned = True
         eng = self._model.engine(frames[0].shape[:2], int(kw.get("imgsz", 384)), float(kw.get("conf", 0.1)),
                                  float(kw.get("iou", 0.7)), 1, max(len(frames), self.timing_config.cycle_frame_num))
-        boxes, counts = eng.detect_views(frames)
+        if lazy:      # whole frames to the device, views cut there
+            boxes, counts = eng.detect_frames([f.frame for f in frames], [f.x0 for f in frames], [f.y0 for f in frames])
+        else:
+            boxes, counts = eng.detect_views(frames)
         rows = []
         for b, c in zip(boxes, counts):
             if c == 0:

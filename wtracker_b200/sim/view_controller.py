@@ -84,6 +84,10 @@ class ViewController(FrameStream):
     def camera_view(self) -> np.ndarray:
         return self._custom_view(*self._camera_size)
 
+    def current_frame(self) -> np.ndarray:
+        """The unpadded frame under the cursor (cached by the stream): what the CUDA crop kernel reads."""
+        return FrameStream.read(self)
+
     def micro_view(self) -> np.ndarray:
         return self._custom_view(*self._micro_size)
 
