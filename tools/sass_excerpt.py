@@ -24,12 +24,13 @@ for line in out.splitlines():
         funcs[cur].append(line)
 demangled = subprocess.run(["cu++filt"] + list(funcs), capture_output=True, text=True).stdout.splitlines()
 names = dict(zip(funcs, demangled)) if len(demangled) == len(funcs) else {k: k for k in funcs}
+names = {k: v.replace("(int)", "").replace("(bool)", "").replace("wt::<unnamed>::", "") for k, v in names.items()}
 MN = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "SYNCS", "MUFU.TANH", "FFMA2"]
 print(f"# cuobjdump -sass {LIB}   (arch {arch}); mnemonic counts per kernel")
 print(f"{'kernel':86s} {'instr':>6} " + " ".join(f"{m:>10s}" for m in MN))
 tot = collections.Counter()
 for f, lines in funcs.items():
-    n = names[f].replace("wt::(anonymous namespace)::", "").replace("(wt::(anonymous namespace)::ConvTcParams)", "").replace("void ", "")
+    n = names[f].replace("(ConvTcParams)", "").replace("void ", "")
     c = {m: sum(1 for l in lines if re.search(r"\b" + re.escape(m), l)) for m in MN}
     for m in MN:
         tot[m] += c[m]
