@@ -80,6 +80,7 @@ class OracleYoloController(YoloController):
 
         self._camera_frames = deque(maxlen=timing_config.cycle_frame_num)
         self._oracle = Y.YoloOracle(oracle_model(), imgsz, max_det=1)
+        self.lazy_views = False      # the oracle takes cropped views, as the reference's controller buffers them
 
     def predict(self, frames):
         return self._oracle.predict(list(frames))

@@ -2,7 +2,11 @@
 Usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.summary.txt"""
 import csv, subprocess, sys
 rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # already a raw page (ncu --csv --page raw --log-file): skip ncu's ==PROF== lines
+    lines = open(rep).read().splitlines()
+    out = "\n".join(lines[next(i for i, l in enumerate(lines) if l.startswith('"ID"')):])
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}
@@ -32,5 +36,5 @@ if len(sys.argv) > 2:      # write the per-step DRAM traffic for bench.py's roof
     batch, imgsz = int(sys.argv[3]), int(sys.argv[4])
     json.dump({"dram_bytes_per_step": int((tot_rd + tot_wr) * 1e6), "launches": len(rows) - 2, "batch": batch, "imgsz": imgsz,
                "source": rep, "how": "sum of dram__bytes_read.sum + dram__bytes_write.sum over every conv launch of ONE timed step "
-               "(ncu --set full --clock-control none -k regex:conv_ -s 177 -c 59 python bench.py --steps 2 --warmup 3 --no-cpu-baseline)"},
+               "(tools/gpu_profile_r2.sh: ncu --set full --clock-control none -k regex:conv_ -s 260 -c 52 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --min-seconds 0)"},
               open(sys.argv[2], "w"), indent=1)
