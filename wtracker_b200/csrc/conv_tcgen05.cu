@@ -97,6 +97,9 @@ struct ConvTcParams {
     // 3x3 layers are bound by the L2 -> shared-memory fill, ~86 % of it weights: DESIGN.md), nt accumulators sit side
     // by side in TMEM and an epilogue group drains all of them.
     int nt;
+    // tuning builds: per-CTA event trace (wt_debug_conv_trace): [launch][CTA][4 roles][trace_cap] u64, or nullptr
+    unsigned long long* trace;
+    int trace_cap;
     // halo kernel: images interleaved per tile (IL template parameter, 1 | 2).  il == 2: the output / residual tensor maps
     // list (channel, x, image, row), the tile is tw x th x 2 with th = 8.
     int il;
@@ -134,6 +137,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+
+// Event trace of one warp role of one CTA (tuning builds only; compiled to nothing in the product library).  Slot 0 holds
+// %globaltimer and slot 1 the SM's clock64 at the same moment (aligns the CTAs of a launch and the launches of a
+// forward); every later slot is tag << 56 | value << 40 | clock64 (40 bits).  tools/gpu_conv_trace.py captures one forward,
+// tools/conv_trace_report.py turns it into a per-launch table (profiles/r02_conv_trace.txt).
+#ifdef WT_TUNING_KNOBS
+struct Tracer {
+    unsigned long long* p;
+    int n, cap;
+    __device__ __forceinline__ Tracer(const ConvTcParams& prm, int role, bool writer) {
+        p = (prm.trace && writer) ? prm.trace + (size_t(blockIdx.x) * 4 + role) * prm.trace_cap : nullptr;
+        n = 0;
+        cap = prm.trace_cap;
+        if (p) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p[0] = gt;
+            p[1] = static_cast<unsigned long long>(clock64());
+            n = 2;
+        }
+    }
+    __device__ __forceinline__ void ev(uint32_t tag, uint32_t val = 0) {
+        if (p && n < cap)
+            p[n++] = (static_cast<unsigned long long>(tag) << 56) | (static_cast<unsigned long long>(val & 0xFFFFu) << 40) |
+                     (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFFFull);
+    }
+    __device__ __forceinline__ long long now() const { return p ? clock64() : 0; }
+    __device__ __forceinline__ void ev_smid(uint32_t tag) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        ev(tag, smid);
+    }
+};
+#else
+struct Tracer {
+    __device__ __forceinline__ Tracer(const ConvTcParams&, int, bool) {}
+    __device__ __forceinline__ void ev(uint32_t, uint32_t = 0) {}
+    __device__ __forceinline__ long long now() const { return 0; }
+    __device__ __forceinline__ void ev_smid(uint32_t) {}
+};
+#endif
 
 // Work item t -> (N block, pixel patch origin).
 struct TileCoord {
@@ -272,7 +316,9 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
     uint32_t unit_counter = 0;
     int it = g;
     const int first = blockIdx.x, step = gridDim.x;
+    Tracer tr(p, 2 + g, store_thread);
     ptx::grid_dependency_wait();   // residual loads and output stores come after the previous kernel
+    tr.ev(1);
     for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
         const TileCoord tc = decode_tile(p, tile);
         const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
@@ -292,8 +338,10 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             ptx::mbar_wait(&add_full[g], aphase);
         }
 
+        tr.ev(19, it);
         ptx::mbar_wait(&tfull_bar[g], aphase);
         ptx::tc_fence_after();
+        tr.ev(20, it);
 
 #pragma unroll 1
         for (int su = 0; su < NT * kUnits; ++su) {
@@ -439,8 +487,10 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
             }
             ++unit_counter;
         }
+        tr.ev(21, it);
     }
     if (store_thread) ptx::tma_store_wait<0>();
+    tr.ev(22);
 }
 
 // Chained form (ConvTcParams.chain, n_blocks == 1, bf16 in / out, BN = 64 | 128).  Per tile the group
@@ -789,6 +839,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvTcParams& p, uint8_t* sS
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
     using L = SmemLayout<BN, BK>;
+    Tracer tr0(p, 0, threadIdx.x == 0);   // (tuning builds) slot 0 / 1 = kernel entry
+    tr0.ev_smid(32);
     const int first = blockIdx.x, step = gridDim.x;
     const int kStages = p.stages;
     constexpr int kRowBytes = L::kRowBytes;
@@ -866,6 +918,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tr0.ev(30);
     // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
     // previous kernel; the next kernel may start its own prologue now.  Activations are only touched after
     // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
@@ -913,12 +966,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 ptx::tma_load_2d(const_cast<uint8_t*>(sW2) + kb * (BN * 128), &p.tmB2, w2_full, kb * 64, 0);
         }
         __syncwarp();
+        Tracer& tr = tr0;
         ptx::grid_dependency_wait();
+        tr.ev(1);
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = first; tile < p.num_tiles; tile += step) {
             const TileCoord tc = decode_tile(p, tile);
             const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
+            tr.ev(2);
             for (int tap = 0; tap < taps; ++tap) {
                 const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
                 int ax, ay, mapi;
@@ -947,6 +1003,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                 }
             }
+            tr.ev(3);
         }
     } else if (warp < kFirstEpiWarp) {
         // ------------------------------------------------------------------ MMA issuer (warp 1; warp 2 idles here)
@@ -963,6 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = 0;
+            Tracer tr(p, 1, true);
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
                 const int ab = it & 1;
                 const uint32_t d_tmem = tmem_base + ab * BN;
@@ -970,10 +1028,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 int stage = int(g0 % uint32_t(kStages));
                 uint32_t phase = (g0 / uint32_t(kStages)) & 1u;
                 uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
+                tr.ev(10, it);
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 ptx::tc_fence_after();
+                tr.ev(11, it);
+                long long wf = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    const long long t0 = tr.now();
                     ptx::mbar_wait(&full_bar[stage], phase);
+                    wf += tr.now() - t0;
                     ptx::tc_fence_after();
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
@@ -992,11 +1055,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                 }
                 ptx::umma_commit(&tfull_bar[ab]);
+                tr.ev(13, uint32_t(wf >> 4));
+                tr.ev(14, it);
             }
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 3..18)
         conv_epilogue<BN>(p, sStage, sBias, tfull_bar, tempty_bar, res_bar, tmem_base, warp, lane, sAdd,
                               add_full, add_empty, chain_bars);
     }
@@ -1061,6 +1126,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     static_assert(IL == 1 || (IL == 2 && !S2), "interleaved tiles: stride 1, single-CTA MMAs");
     static_assert(NT == 1 || (2 * NT * BN <= 512), "tile groups: single-CTA MMAs, 2 x NT accumulators in TMEM");
     using L = HaloSmem<BN, BK, S2, IL>;
+    Tracer tr0(p, 0, threadIdx.x == 0);   // (tuning builds) slot 0 / 1 = kernel entry
+    tr0.ev_smid(32);
     constexpr int kARowBytes = L::kARowBytes;
     constexpr int kTapRowPitch = kHaloW * IL;        // pixels between vertically adjacent taps in the halo tile
     const int first = blockIdx.x, step = gridDim.x;
@@ -1149,6 +1216,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tr0.ev(30);
     // Programmatic dependent launch: everything above (barriers, TMEM, bias = constants) overlapped the tail of the
     // previous kernel; the next kernel may start its own prologue now.  Activations are only touched after
     // grid_dependency_wait() (producer and epilogue warps; the MMA warps never touch global memory).
@@ -1182,7 +1250,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             ptx::tma_load_2d(const_cast<uint8_t*>(sW2b), &p.tmB2b, w2_full, kCatC, 0);
         }
         __syncwarp();
+        Tracer& tr = tr0;
         ptx::grid_dependency_wait();
+        tr.ev(1);
         int sa = 0, sb = 0;
         uint32_t pa = 0, pb = 0;
         for (int tile = first; tile < p.num_tiles; tile += step) {
@@ -1206,6 +1276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     }
                 }
                 __syncwarp();
+                tr.ev(2, cb);
                 if (++sa == kAStages) { sa = 0; pa ^= 1; }
                 if (p.resident && tile != first) continue;   // weights already in shared memory
                 for (int tap = 0; tap < 9; ++tap) {
@@ -1217,6 +1288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     __syncwarp();
                     if (++sb == kBStages) { sb = 0; pb ^= 1; }
                 }
+                tr.ev(3, cb);
             }
         }
     } else if (warp < kFirstEpiWarp) {
@@ -1232,6 +1304,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             const uint32_t a_hi = uint32_t(a_desc0 >> 32), b_hi = uint32_t(b_desc0 >> 32);
             const uint32_t a_lo0 = uint32_t(a_desc0), b_lo0 = uint32_t(b_desc0);
             int it = 0;
+            Tracer tr(p, 1, true);
             if (kBStages == 9) {
                 // Weight ring of exactly nine slots (resident weights, or the host chose 9 stages): slot == tap, so
                 // every weight descriptor and barrier address in the unrolled tap loop is base + immediate and the
@@ -1245,15 +1318,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     uint32_t pa = (ga / uint32_t(kAStages)) & 1u;
                     uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4);
                     const bool wait_b = !p.resident || it == 0;
+                    tr.ev(10, it);
                     ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
+                    tr.ev(11, it);
                     for (int cb = 0; cb < p.cin_blocks; ++cb) {
                         const uint32_t pb = (ga + cb) & 1u;
                         ptx::mbar_wait(&afull[sa], pa);
                         ptx::tc_fence_after();
+                        tr.ev(12, cb);
+                        long long wb = 0;
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
                             if (wait_b) {
+                                const long long t0 = tr.now();
                                 ptx::mbar_wait(&bfull[tap], pb);
+                                wb += tr.now() - t0;
                                 ptx::tc_fence_after();
                             }
                             const int kh = tap / 3, kw = tap - kh * 3;
@@ -1274,10 +1353,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                             }
                         }
                         ptx::umma_commit(&aempty[sa]);
+                        tr.ev(13, uint32_t(wb >> 4));
                         a_lo += kAStageBytes >> 4;
                         if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                     }
                     ptx::umma_commit(&tfull_bar[ab]);
+                    tr.ev(14, it);
                 }
             } else
             for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
@@ -1296,14 +1377,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                 uint32_t a_lo = a_lo0 + sa * (kAStageBytes >> 4), b_lo = b_lo0 + sb * (L::kBBytes >> 4);
                 // resident weights: waited for once, all nine taps (phase 0 of each slot)
                 const bool wait_b = !p.resident || it == 0;   // (resident: the first tile of each issuer)
+                tr.ev(10, it);
                 ptx::mbar_wait(&tempty_bar[ab], ((it >> 1) & 1) ^ 1);
+                tr.ev(11, it);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
                     ptx::mbar_wait(&afull[sa], pa);
                     ptx::tc_fence_after();
+                    tr.ev(12, cb);
+                    long long wb = 0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         if (wait_b) {
+                            const long long t0 = tr.now();
                             ptx::mbar_wait(&bfull[sb], pb);
+                            wb += tr.now() - t0;
                             ptx::tc_fence_after();
                         }
                         const int kh = tap / 3, kw = tap - kh * 3;
@@ -1325,10 +1412,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                         if (++sb == kBStages) { sb = 0; pb ^= 1; b_lo = b_lo0; }
                     }
                     ptx::umma_commit(&aempty[sa]);
+                    tr.ev(13, uint32_t(wb >> 4));
                     a_lo += kAStageBytes >> 4;
                     if (++sa == kAStages) { sa = 0; pa ^= 1; a_lo = a_lo0; }
                 }
                 ptx::umma_commit(&tfull_bar[ab]);
+                tr.ev(14, it);
             }
         }
         __syncwarp();
@@ -2095,8 +2184,30 @@ static int launch_halo(const ConvTcParams& prm, int smem, int grid, cudaStream_t
     return launch_kernel(conv_halo_kernel<BN, BK, S2, NT, IL>, &opt_in, prm, smem, grid, stream);
 }
 
+#ifdef WT_TUNING_KNOBS
+// Event trace of the tcgen05 conv launches (tuning builds): launch i since the call writes region i of `buf`
+// ([max_launches][148 CTAs][4 roles][cap] u64, zero-filled by the caller); nullptr switches tracing off.
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0, g_trace_max = 0, g_trace_next = 0;
+extern "C" int wt_debug_conv_trace(unsigned long long* buf, int cap, int max_launches) {
+    g_trace_buf = buf;
+    g_trace_cap = cap;
+    g_trace_max = max_launches;
+    g_trace_next = 0;
+    return 0;
+}
+#endif
+
 int conv_tc_launch(const ConvTcPlan* pl, int n_images, int sm_count, cudaStream_t stream) {
     ConvTcParams prm = pl->prm;
+#ifdef WT_TUNING_KNOBS
+    prm.trace = nullptr;
+    prm.trace_cap = g_trace_cap;
+    if (g_trace_buf && g_trace_next < g_trace_max) {
+        prm.trace = g_trace_buf + size_t(g_trace_next) * 148 * 4 * g_trace_cap;
+        ++g_trace_next;
+    }
+#endif
     const int tiles_n = ceil_div(n_images, prm.tn * prm.nt);   // (halo kernel: groups of nt images)
     prm.num_tiles = pl->pix_per_image_tiles * tiles_n * prm.n_blocks;   // work items
     prm.n_images = n_images;
