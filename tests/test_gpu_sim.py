@@ -91,11 +91,13 @@ class ViewRecorder(Recorder):
 
     def __init__(self, inner):
         super().__init__(inner)
-        self.views = []
+        self.views, self.det_pos = [], []
 
     def provide_movement_vector(self, sim):
-        lv = self.inner._camera_frames[-self.inner.timing_config.pred_frame_num]
+        pfn = self.inner.timing_config.pred_frame_num
+        lv = self.inner._camera_frames[-pfn]
         self.views.append(np.ascontiguousarray(np.asarray(lv)))
+        self.det_pos.append(self.pos[-pfn])      # platform position when that view was taken
         return super().provide_movement_vector(sim)
 
 
@@ -105,7 +107,7 @@ MARGIN, BOX_TOL = 2e-2, 0.5      # as in test_gpu_parity64.py
 @torch.no_grad()
 def oracle_candidates(view, imgsz=384, conf_thres=0.1):
     """fp32 oracle on one view: (confidence of every anchor, kept anchor or -1, its xyxy box in view pixels, whether the
-    decision is AMBIGUOUS: another anchor within MARGIN of the best confidence whose box centre lies more than a pixel
+    decision is AMBIGUOUS: another anchor within MARGIN of the best confidence whose box centre lies more than two pixels
     away — bf16 feature noise, or a one-pixel shift of the crop, may then pick the other box)."""
     x = Y.preprocess([view], imgsz)
     pred = oracle_model()(x)
@@ -117,7 +119,7 @@ def oracle_candidates(view, imgsz=384, conf_thres=0.1):
     box = Y.scale_boxes(x.shape[2:], rows[:, :4], view.shape[:2])[0].numpy()
     near = torch.nonzero(conf > conf[best] - MARGIN).flatten()
     d = (pred[0, :2, near] - pred[0, :2, best:best + 1]).abs().amax(0)
-    ambiguous = bool((d > 1.0).any()) or bool(abs(float(conf[best]) - conf_thres) < MARGIN)
+    ambiguous = bool((d > 2.0).any()) or bool(abs(float(conf[best]) - conf_thres) < MARGIN)
     return conf, best, box, ambiguous
 
 
@@ -129,9 +131,12 @@ def test_closed_loop_yolo_controller_matches_oracle_loop():
     (same anchor: box within 0.5 px, movement vector within one pixel), SWAPPED inside the margin (the oracle scores the
     GPU's anchor within 2e-2 of its own best — test_gpu_parity64.py's accounting) or WRONG.  No cycle may be wrong, at most
     10 % swapped; the counts are printed and written to gpurun_out/closed_loop.json.
-    (2) Free-running: the same loop with the oracle as the detector.  Up to the first cycle whose decision is ambiguous
-    in either loop the vectors agree within one pixel and the positions within two; over the WHOLE run the two platforms
-    stay within a worm box of each other and of the worm (every cycle re-centres: differences must not accumulate)."""
+    (2) Free-running: the same loop with the oracle as the detector.  The two loops see crops that may be a pixel apart
+    (a flipped round()), so they are compared in ABSOLUTE coordinates: where each loop places the worm (platform position
+    of the detected view + movement vector).  On every cycle whose decision is unambiguous in both loops the two places
+    agree within three pixels (one from each round() and one of sub-pixel sensitivity to the shifted crop); at most half of
+    the cycles may be ambiguous (the synthetic net scores neighbouring anchors of one worm within 2e-2 of each other); over the whole run the platforms stay within
+    a worm box of each other (every cycle re-centres: differences must not accumulate) and both end on the worm."""
     import json
     import os
 
@@ -182,11 +187,12 @@ def test_closed_loop_yolo_controller_matches_oracle_loop():
 
     # ---- (2) free-running
     amb_b = [oracle_candidates(v)[3] for v in b.views]
-    first_amb = next((k for k in range(n_cycles) if amb_a[k] or amb_b[k]), n_cycles)
+    amb = np.array(amb_a) | np.array(amb_b)
     va, vb, pa, pb = np.array(a.vec), np.array(b.vec), np.array(a.pos), np.array(b.pos)
+    place = np.abs((np.array(a.det_pos) + va) - (np.array(b.det_pos) + vb)).max(axis=1)     # per cycle
     dv, dp = np.abs(va - vb), np.abs(pa - pb)
-    stats.update(first_ambiguous_cycle=first_amb, ambiguous_cycles=int(np.sum(np.array(amb_a) | np.array(amb_b))),
-                 max_dv_before=int(dv[:first_amb].max(initial=0)), max_dp_before=int(dp[:first_amb * 9].max(initial=0)),
+    stats.update(ambiguous_cycles=int(amb.sum()), place_diff=place.tolist(), ambiguous=amb.astype(int).tolist(),
+                 max_place_diff_unambiguous=int(place[~amb].max(initial=0)), max_place_diff=int(place.max()),
                  max_dv=int(dv.max()), max_dp=int(dp.max()), equal_vectors=float((dv == 0).all(axis=1).mean()))
     print("[closed loop] " + json.dumps(stats))
     os.makedirs("gpurun_out", exist_ok=True)
@@ -195,7 +201,7 @@ def test_closed_loop_yolo_controller_matches_oracle_loop():
     assert not failures, failures[:6]
     assert stats["wrong"] == 0 and stats["swapped"] <= 0.1 * n_cycles, stats
     assert stats["identical"] >= 0.8 * n_cycles, stats
-    assert stats["max_dv_before"] <= 1 and stats["max_dp_before"] <= 2, (stats, a.vec, b.vec)
+    assert stats["max_place_diff_unambiguous"] <= 3 and stats["ambiguous_cycles"] <= n_cycles // 2, (stats, a.vec, b.vec)
     assert stats["max_dp"] <= 16 and stats["equal_vectors"] >= 0.5, (stats, a.vec, b.vec)
     # and both track: the platform ends within a few pixels of the worm head
     for rec in (a, b):
