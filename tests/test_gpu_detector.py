@@ -45,6 +45,21 @@ def test_feature_maps_within_bf16_noise(setup):
         assert err.max() / ref.abs().max() < 0.05, f"{name}: max err {err.max():.4f}"
 
 
+def test_sppf_pool_is_bit_exact(setup):
+    """model.9.m: three cascaded 5 x 5 / stride-1 max pools written beside their input (SPPF).  max() is exact, so the
+    three pooled slices must equal torch's max_pool2d of the kernel's own bf16 input, bit for bit (12 x 12 and 20 x 20)."""
+    from wtracker_b200 import _lib as L
+
+    eng = setup["eng"]
+    op = next(o for o in eng.program.ops if o["kind"] == L.WT_OP_SPPF_POOL)
+    buf = eng.buffer_tensor(op["src"], 4).float().permute(0, 3, 1, 2)          # [n, C, h, w]
+    c, off = op["cin"], op["dst_coff"]
+    x = buf[:, op["src_coff"]: op["src_coff"] + c]
+    for r in range(3):
+        x = torch.nn.functional.max_pool2d(x, 5, 1, 2)
+        assert torch.equal(buf[:, off + r * c: off + (r + 1) * c], x), f"pool {r}"
+
+
 def test_head_logits(setup):
     eng = setup["eng"]
     for lvl, h in enumerate(eng.program.head):

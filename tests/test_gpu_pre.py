@@ -45,6 +45,8 @@ CASES = [  # view (h, w), imgsz
     ((300, 500), 384),    # non-square: resample + 114 padding
     ((251, 251), 384),    # odd size (the ViewController default)
     ((700, 700), 640),    # down-scale
+    ((1000, 1000), 384),  # strong down-scale: the four columns of a work item reach further than two words apart
+    ((1080, 1920), 640),  # the whole frame as the view
 ]
 
 

@@ -327,6 +327,72 @@ __global__ void __launch_bounds__(kPoolThreads * G) sppf_pool_kernel(const __nv_
     }
 }
 
+// Sliding-window form for maps up to 32 x 32 (the SPPF of every supported network size): 4 channel groups per CTA as above,
+// but a thread is a whole ROW of one group in the horizontal passes and a whole COLUMN in the vertical ones and keeps the
+// 5-wide window in registers — one shared-memory load and one store per output and pass instead of five loads (the
+// kernel above is LDS-wavefront bound: ncu, round 2).  m[x] = max(p[x-2], v[x], p[x+1]) with the pair maxima
+// p[x] = max(v[x], v[x+1]) carried along; outside the map the window holds -inf.  Rows are padded to w + 1 pixels so that
+// the two rows (columns) of a quarter-warp fall into different halves of the 32 banks.
+constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16x2 (-inf, -inf)
+
+template <bool kToGlobal>
+__device__ __forceinline__ void pool_slide(const uint4* in, uint4* out, int len, int pitch, __nv_bfloat16* gdst,
+                                           size_t gpitch) {
+    const uint4 neg = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
+    uint4 v0 = in[0];
+    uint4 vp1 = len > 1 ? in[pitch] : neg;
+    uint4 pm2 = neg, pm1 = v0;                  // p[x - 2], p[x - 1] at x = 0 (p[-1] = max(-inf, v[0]))
+    uint4 p0 = max_bf16x8(v0, vp1);             // p[x]
+    for (int x0 = 0; x0 < len; x0 += 4) {
+        uint4 nx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nx[k] = x0 + k + 2 < len ? in[(x0 + k + 2) * pitch] : neg;   // v[x + 2]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = x0 + k;
+            if (x < len) {
+                const uint4 p1 = max_bf16x8(vp1, nx[k]);                  // p[x + 1]
+                const uint4 m = max_bf16x8(max_bf16x8(pm2, v0), p1);
+                out[x * pitch] = m;
+                if (kToGlobal) *reinterpret_cast<uint4*>(gdst + size_t(x) * gpitch) = m;
+                pm2 = pm1; pm1 = p0; p0 = p1;
+                v0 = vp1; vp1 = nx[k];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sppf_pool_slide_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
+                                                              __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c,
+                                                              int h, int w) {
+    extern __shared__ uint4 pool_smem[];
+    constexpr int G = 4;
+    const int pw = w + 1, hw = h * w;
+    uint4* cur = pool_smem;                   // [h][pw][G]
+    uint4* tmp = pool_smem + h * pw * G;
+    const int n = blockIdx.y;
+    const int g = threadIdx.x & (G - 1), u = threadIdx.x >> 2, units = blockDim.x >> 2;
+    const int c0 = (blockIdx.x * G + g) * kPoolCg;
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    // every thread of the CTA loads (the sliding passes below occupy only max(h, w) x 4 of them): independent loads,
+    // four in flight per thread
+#pragma unroll 4
+    for (int i = u; i < hw; i += units) {
+        const int y = i / w;
+        cur[(y * pw + (i - y * w)) * G + g] = __ldg(reinterpret_cast<const uint4*>(src + (size_t(n) * hw + i) * sct + scoff + c0));
+    }
+    __syncthreads();
+    for (int round = 0; round < 3; ++round) {
+        if (u < h) pool_slide<false>(cur + u * pw * G + g, tmp + u * pw * G + g, w, G, nullptr, 0);
+        __syncthreads();
+        if (u < w)
+            pool_slide<true>(tmp + u * G + g, cur + u * G + g, h, pw * G,
+                             dst + (size_t(n) * hw + u) * dct + dcoff + round * c + c0, size_t(w) * dct);
+        __syncthreads();
+    }
+}
+
 // Any map size (one channel group per CTA, coordinates recomputed per pass): used above 512 pixels.
 __global__ void __launch_bounds__(kPoolThreads) sppf_pool_generic_kernel(const __nv_bfloat16* __restrict__ src, int sct,
                                                                          int scoff, __nv_bfloat16* __restrict__ dst,
@@ -416,11 +482,21 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
                "SPPF channels and slices must be multiples of 8");
     WT_REQUIRE(src.h == dst.h && src.w == dst.w, "SPPF keeps the spatial size");
     WT_REQUIRE(src.dtype == WT_DT_BF16 && dst.dtype == WT_DT_BF16, "SPPF works on bf16");
+    if (n_images == 0) return 0;
+    if (src.h <= 32 && src.w <= 32 && c % (4 * kPoolCg) == 0) {   // every YOLOv8 SPPF up to 1024 x 1024 inputs
+        const size_t smem = size_t(src.h) * (src.w + 1) * 4 * sizeof(uint4) * 2;
+        static SmemOptIn opt_in;
+        WT_CHECK_CUDA(opt_in_smem(sppf_pool_slide_kernel, opt_in, smem));
+        WT_CHECK_CUDA(launch_pdl(sppf_pool_slide_kernel, dim3(c / (kPoolCg * 4), n_images), dim3(256), smem,
+                                 stream, static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
+                                 static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w));
+        WT_LAUNCHED();
+        return 0;
+    }
     const bool small = src.h * src.w <= kPoolIter * kPoolThreads;
     const int G = (small && c % (4 * kPoolCg) == 0) ? 4 : 1;
     const size_t smem = size_t(src.h) * src.w * sizeof(uint4) * 2 * G;
     WT_REQUIRE(smem <= 200 * 1024, "SPPF feature map too large for the shared-memory pool kernel");
-    if (n_images == 0) return 0;
     auto* kernel = !small ? sppf_pool_generic_kernel : (G == 4 ? sppf_pool_kernel<4> : sppf_pool_kernel<1>);
     static SmemOptIn opt_in[3];
     WT_CHECK_CUDA(opt_in_smem(kernel, opt_in[!small ? 2 : (G == 4)], smem));

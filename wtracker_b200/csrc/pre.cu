@@ -185,26 +185,91 @@ __global__ void __launch_bounds__(256) pre_crop_kernel(const PreParams p) {
     for (int r = 0; r < kCropRows; ++r) *reinterpret_cast<uint4*>(o + size_t(r) * p.lb.dst_w) = v[r];
 }
 
-// Resize path of the product (u8-only) output.  The kernel above gives every thread 16 adjacent output pixels, so a
-// warp's byte gathers touch ~4 cache lines per load and the resize ran at 3-5 % of HBM bandwidth (L1 wavefront
-// bound).  Here one CTA produces kResizeRows output rows of one image: the source rows it needs are staged ONCE in
-// shared memory with coalesced, clamp-addressed loads (== BORDER_REPLICATE), a thread owns output COLUMNS (its
-// horizontal taps and weights stay in registers) and walks the rows, so shared-memory reads and global stores of a
-// warp are contiguous.  Same integer arithmetic as above: bit-exact against cv2.resize's fixed-point model.
-constexpr int kResizeThreads = 256;
-constexpr int kResizeRows = 16;
+// Resize path of the product (u8-only) output.  One CTA produces kResizeRows output rows of one image.
+//  * The source rows it needs are staged ONCE in shared memory, clamp-addressed (== BORDER_REPLICATE): 32-bit loads
+//    re-aligned with a funnel shift where the view lies inside the frame, byte loads where it hangs over the border.
+//  * A thread owns 4 adjacent output columns over kResizeSpan consecutive output rows.  Its horizontal taps live in
+//    registers: per staged row two 32-bit shared-memory loads cover the <= 8 source bytes the four columns touch, one
+//    PRMT per column puts its (left, right) byte pair in place and one DP2A applies the two 11-bit weights.  The
+//    horizontal results of the previous output row's tap pair are kept: when shrinking, last row's bottom tap is this
+//    row's top tap (one new row per output row); when enlarging, half of the rows repeat the pair (nothing new).
+//    The vertical pass is two IMAD.HI per pixel (b << 16 pre-shifted per row) and one 32-bit store per row.
+//  * ncu (round 2, profiles/r02_simt_resize_pool.summary.txt): the kernel is instruction-issue bound (75 % of the issue
+//    slots); the first form of this design spent 105 instructions per 4 pixels on cache bookkeeping and 64-bit store
+//    addresses, this one ~45.
+// Same integer arithmetic as pre_kernel: bit-exact against cv2.resize's fixed-point model.
+constexpr int kResizeRows = 32;
+constexpr int kResizeSpan = 16;
 
-__global__ void __launch_bounds__(kResizeThreads) pre_resize_kernel(const PreParams p, int pitch) {
-    extern __shared__ uint8_t s_rows[];   // [rows of this tile][pitch]
-    __shared__ int s_r0[kResizeRows], s_r1[kResizeRows], s_b0[kResizeRows], s_b1[kResizeRows];
+__device__ __forceinline__ uint32_t dp2a_u(uint32_t a, uint32_t b, uint32_t c) {   // a.lo16 * b.byte0 + a.hi16 * b.byte1 + c
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct ResizeTaps {
+    uint32_t coef[4];   // a0 | a1 << 16
+    uint32_t sel[4];    // PRMT selector: byte 0 = left tap, byte 1 = right tap (offsets from the item's first word)
+    int sx[4], sx1[4];  // byte path (taps further apart than two words)
+    int word;           // first 32-bit word of the row the item reads
+    bool packed;
+    uint32_t in_mask;   // bit i: column i lies inside the resized image
+};
+
+// horizontal pass of one staged row for the item's four columns: (s0 * a0 + s1 * a1) >> 4, the form the vertical pass uses
+__device__ __forceinline__ void resize_hrow(const uint8_t* s_rows, int r, const ResizeTaps& t, int h[4]) {
+    if (t.packed) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(s_rows + r) + t.word;
+        const uint32_t lo = q[0], hi = q[1];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = int(dp2a_u(t.coef[i], __byte_perm(lo, hi, t.sel[i]), 0u) >> 4);
+    } else {
+        const uint8_t* q = s_rows + r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            h[i] = (int(q[t.sx[i]]) * int(t.coef[i] & 0xFFFFu) + int(q[t.sx1[i]]) * int(t.coef[i] >> 16)) >> 4;
+    }
+}
+
+__device__ __forceinline__ ResizeTaps resize_taps(const wt_letterbox& lb, int X0) {
+    ResizeTaps t;
+    t.in_mask = 0u;
+    int lo_b = 1 << 30, hi_b = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rx = X0 + i - lb.pad_left;
+        t.sx[i] = t.sx1[i] = 0;
+        t.coef[i] = 0u;
+        if (rx >= 0 && rx < lb.new_w) {
+            t.in_mask |= 1u << i;
+            t.sx[i] = lb.xofs[rx];
+            t.sx1[i] = t.sx[i] + 1 < lb.src_w ? t.sx[i] + 1 : t.sx[i];
+            t.coef[i] = uint32_t(uint16_t(lb.xcoef[2 * rx])) | (uint32_t(uint16_t(lb.xcoef[2 * rx + 1])) << 16);
+            lo_b = min(lo_b, t.sx[i]);
+            hi_b = max(hi_b, t.sx1[i]);
+        }
+    }
+    t.word = hi_b >= 0 ? lo_b >> 2 : 0;
+    t.packed = hi_b < 0 || hi_b - (t.word << 2) < 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)   // (upper selector bytes: don't care; columns outside the image are overwritten with 114)
+        t.sel[i] = t.packed ? (uint32_t(t.sx[i] - (t.word << 2)) & 7u) | ((uint32_t(t.sx1[i] - (t.word << 2)) & 7u) << 4) | 0x4400u : 0x4400u;
+    return t;
+}
+
+__global__ void __launch_bounds__(256) pre_resize_kernel(const PreParams p, int pitch) {
+    extern __shared__ __align__(16) uint8_t s_rows[];   // [rows of this tile][pitch]
+    __shared__ int4 s_row[kResizeRows];                 // per output row: (top row offset | -1, bottom row offset, b0 << 16, b1 << 16)
     const wt_letterbox& lb = p.lb;
     const int img = blockIdx.y, Y0 = blockIdx.x * kResizeRows;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // thread = (column group lane, row span): blockDim.y == kResizeRows / kResizeSpan
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warps = (blockDim.x * blockDim.y) >> 5;
     const int rows_here = min(kResizeRows, lb.dst_h - Y0);
     const uint8_t* frame = p.frames + size_t(clampi(p.frame_idx[img], 0, p.n_frames - 1)) * p.fh * p.fw;
     const int cx = p.crop_x[img], cy = p.crop_y[img];
 
-    // view rows this tile reads: [vbase, vtop]
+    // view rows this tile reads: [vbase, vbase + nrows)
     const int ry_lo = max(Y0 - lb.pad_top, 0), ry_hi = min(Y0 + rows_here - lb.pad_top, lb.new_h) - 1;
     int vbase = 0, nrows = 0;
     if (ry_lo <= ry_hi) {
@@ -213,45 +278,77 @@ __global__ void __launch_bounds__(kResizeThreads) pre_resize_kernel(const PrePar
     }
     if (tid < rows_here) {
         const int ry = Y0 + tid - lb.pad_top;
-        int r0 = -1, r1 = -1, b0 = 0, b1 = 0;
+        int4 e = make_int4(-1, -1, 0, 0);
         if (ry >= 0 && ry < lb.new_h) {
             const int sy = lb.yofs[ry];
-            r0 = (clampi(sy, 0, lb.src_h - 1) - vbase) * pitch;
-            r1 = (clampi(sy + 1, 0, lb.src_h - 1) - vbase) * pitch;
-            b0 = lb.ycoef[2 * ry];
-            b1 = lb.ycoef[2 * ry + 1];
+            e.x = (clampi(sy, 0, lb.src_h - 1) - vbase) * pitch;
+            e.y = (clampi(sy + 1, 0, lb.src_h - 1) - vbase) * pitch;
+            e.z = int(lb.ycoef[2 * ry]) << 16;       // (b * t) >> 16 == umulhi(b << 16, t): 0 <= b <= 2048, t < 2^15
+            e.w = int(lb.ycoef[2 * ry + 1]) << 16;
         }
-        s_r0[tid] = r0; s_r1[tid] = r1; s_b0[tid] = b0; s_b1[tid] = b1;
+        s_row[tid] = e;
     }
-    for (int r = warp; r < nrows; r += kResizeThreads / 32) {
+    // the taps of this thread's first column group: table loads in flight while the rows are staged
+    const int groups = lb.dst_w >> 2;
+    ResizeTaps t = resize_taps(lb, min(int(threadIdx.x), groups - 1) << 2);
+    // the whole staged row (pitch bytes + one word of slack) lies inside the frame row: word loads
+    const bool x_in = cx >= 0 && cx + pitch + 4 <= p.fw;
+    for (int r = warp; r < nrows; r += warps) {
         const uint8_t* srow = frame + size_t(clampi(cy + vbase + r, 0, p.fh - 1)) * p.fw;
-        for (int c = lane; c < lb.src_w; c += 32) s_rows[r * pitch + c] = __ldg(srow + clampi(cx + c, 0, p.fw - 1));
+        if (x_in) {
+            const uint8_t* src = srow + cx;
+            const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(src - m);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s_rows + r * pitch);
+            for (int w = lane; w < (pitch >> 2); w += 32) dst[w] = __funnelshift_r(__ldg(base + w), __ldg(base + w + 1), m * 8u);
+        } else {
+            for (int c = lane; c < lb.src_w; c += 32) s_rows[r * pitch + c] = __ldg(srow + clampi(cx + c, 0, p.fw - 1));
+        }
     }
     __syncthreads();
 
-    uint8_t* out = p.out_u8 + (size_t(img) * lb.dst_h + Y0) * lb.dst_w;
-    for (int x = tid; x < lb.dst_w; x += kResizeThreads) {
-        const int rx = x - lb.pad_left;
-        const bool col_in = rx >= 0 && rx < lb.new_w;
-        int sx = 0, sx1 = 0, a0 = 0, a1 = 0;
-        if (col_in) {
-            sx = lb.xofs[rx];
-            sx1 = sx + 1 < lb.src_w ? sx + 1 : sx;
-            a0 = lb.xcoef[2 * rx];
-            a1 = lb.xcoef[2 * rx + 1];
-        }
-#pragma unroll 4
-        for (int j = 0; j < rows_here; ++j) {
-            const int r0 = s_r0[j];
-            int v = 114;
-            if (col_in && r0 >= 0) {
-                const uint8_t* q0 = s_rows + r0;
-                const uint8_t* q1 = s_rows + s_r1[j];
-                const int h0 = int(q0[sx]) * a0 + int(q0[sx1]) * a1;
-                const int h1 = int(q1[sx]) * a0 + int(q1[sx1]) * a1;
-                v = clampi((((s_b0[j] * (h0 >> 4)) >> 16) + ((s_b1[j] * (h1 >> 4)) >> 16) + 2) >> 2, 0, 255);
+    const int j0 = threadIdx.y * kResizeSpan, j_end = min(rows_here, j0 + kResizeSpan);
+    const int out_pitch = lb.dst_w >> 2;    // in 32-bit words
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        if (g != int(threadIdx.x)) t = resize_taps(lb, g << 2);
+        uint32_t* o = reinterpret_cast<uint32_t*>(p.out_u8 + (size_t(img) * lb.dst_h + Y0 + j0) * lb.dst_w) + g;
+        // (ka, ha) / (kb, hb): staged-row offset and horizontal result of the previous output row's top / bottom tap
+        int ka = -1, kb = -1, ha[4] = {0, 0, 0, 0}, hb[4] = {0, 0, 0, 0};
+        for (int j = j0; j < j_end; ++j, o += out_pitch) {
+            const int4 e = s_row[j];
+            uint32_t v = 0x72727272u;   // 114 x 4
+            if (e.x >= 0 && t.in_mask) {
+                if (e.x != ka || e.y != kb) {      // (equal: an enlarging resize repeats the tap pair)
+                    if (e.x == kb) {               // the usual step: last row's bottom tap is this row's top tap
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ha[i] = hb[i];
+                    } else {
+                        resize_hrow(s_rows, e.x, t, ha);
+                    }
+                    if (e.y == e.x) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) hb[i] = ha[i];
+                    } else {
+                        resize_hrow(s_rows, e.y, t, hb);
+                    }
+                    ka = e.x; kb = e.y;
+                }
+                // weights are >= 0 and sum to 2048 +- 1 per axis, so ((b0 t0 >> 16) + (b1 t1 >> 16) + 2) >> 2 <= 255: no clamp
+                uint32_t px[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t acc = __umulhi(uint32_t(e.z), uint32_t(ha[i])) + 2u;
+                    acc = __umulhi(uint32_t(e.w), uint32_t(hb[i])) + acc;
+                    px[i] = acc >> 2;
+                }
+                if (t.in_mask != 0xFu) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (!((t.in_mask >> i) & 1u)) px[i] = 114u;
+                }
+                v = __byte_perm(__byte_perm(px[0], px[1], 0x0040u), __byte_perm(px[2], px[3], 0x0040u), 0x5410u);
             }
-            out[size_t(j) * lb.dst_w + x] = uint8_t(v);
+            *o = v;
         }
     }
 }
@@ -294,16 +391,21 @@ extern "C" int wt_preprocess(const uint8_t* frames, int n_frames, int frame_h, i
         WT_LAUNCHED();
         return 0;
     }
-    if (resize && out_u8 && !out_f32) {
-        // rows of the view one 16-row output tile can touch (+1 for the second tap, +2 for rounding at both ends)
+    if (resize && out_u8 && !out_f32 && lb->dst_w % 4 == 0) {
+        // rows of the view one output tile can touch (+1 for the second tap, +2 for rounding at both ends)
         const int max_rows = std::min(lb->src_h, ((kResizeRows - 1) * lb->src_h + lb->new_h - 1) / lb->new_h + 3);
-        const int pitch = (lb->src_w + 15) & ~15;
+        const int pitch = (lb->src_w + 4 + 15) & ~15;     // (a word of slack: an item reads two words from its first tap)
         const int smem = max_rows * pitch;
         if (smem <= 200 * 1024) {
             static SmemOptIn opt_in;
             WT_CHECK_CUDA(opt_in_smem(pre_resize_kernel, opt_in, 200 * 1024));
+            // thread = (column group lane, 16-row span): 384 wide -> 96 x 2 threads with one column group each, 640 wide ->
+            // 96 x 2 threads with one or two (taps are loaded per column group and amortised over the 16 rows of a span)
+            const int groups = lb->dst_w / 4;
+            const int iters = (groups + 127) / 128;
+            dim3 block(std::min(128, (((groups + iters - 1) / iters) + 31) & ~31), kResizeRows / kResizeSpan);
             dim3 rgrid((lb->dst_h + kResizeRows - 1) / kResizeRows, n);
-            pre_resize_kernel<<<rgrid, kResizeThreads, smem, static_cast<cudaStream_t>(stream)>>>(p, pitch);
+            pre_resize_kernel<<<rgrid, block, smem, static_cast<cudaStream_t>(stream)>>>(p, pitch);
             WT_LAUNCHED();
             return 0;
         }
