@@ -60,6 +60,26 @@ def test_sppf_pool_is_bit_exact(setup):
         assert torch.equal(buf[:, off + r * c: off + (r + 1) * c], x), f"pool {r}"
 
 
+def test_graph_replay_equals_eager_launches(setup):
+    """Small host batches replay a CUDA graph of the three stages (launch-bound per-cycle calls of the simulator): the
+    replayed path must return exactly what the eager launches return, on inputs that change between replays, and the
+    graph must really have been captured (no silent eager fallback)."""
+    from wtracker_b200.detector.engine import DetectorEngine
+
+    eng = DetectorEngine(synthetic_sd(), (setup["view"], setup["view"]), setup["imgsz"], batch=4, max_det=1)
+    views = setup["views"]
+    eng.graph_max_batch = 0
+    want = [eng.detect_views([v]) for v in views] + [eng.detect_views(views[:3])]
+    eng.graph_max_batch = 16
+    for _ in range(2):                                   # eager warm-up call, capturing call, then replays
+        eng.detect_views([views[0]])
+        eng.detect_views(views[:3])
+    got = [eng.detect_views([v]) for v in views] + [eng.detect_views(views[:3])]
+    assert sum(isinstance(g, torch.cuda.CUDAGraph) for g in eng._graphs.values()) == 2
+    for (gb, gc), (wb, wc) in zip(got, want):
+        assert np.array_equal(gc, wc) and np.array_equal(gb, wb)
+
+
 def test_head_logits(setup):
     eng = setup["eng"]
     for lvl, h in enumerate(eng.program.head):

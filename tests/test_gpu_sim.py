@@ -228,6 +228,17 @@ def test_lazy_views_equal_buffered_views():
         lv = LazyView(frames[3], origin[0], origin[1], 360, 360)
         want = synth.camera_view(frames[3], (origin[0] + 180, origin[1] + 180), 360)
         assert np.array_equal(np.asarray(lv), want) and lv.shape == (360, 360)
+    # frame ingest at the borders: the window of the frame + the device crop must feed the net exactly the buffered view
+    eng = runs[0].inner._model.engine((360, 360), 384, 0.1, 0.7, 1, t.cycle_frame_num)
+    origins = [(-40, 500), (1700, -25), (800, 900), (300, 200), (-400, -400), (1919, 1079), (1560, 720), (0, 0)]
+    views = [synth.camera_view(frames[i % 6], (x + 180, y + 180), 360) for i, (x, y) in enumerate(origins)]
+    for chunk in (slice(0, 1), slice(0, 8), slice(3, 6)):
+        fb, fc = eng.detect_frames([frames[i % 6] for i in range(8)][chunk], [o[0] for o in origins][chunk],
+                                   [o[1] for o in origins][chunk])
+        net_in = eng.input_view[: chunk.stop - chunk.start].cpu().numpy().copy()
+        vb, vc = eng.detect_views(views[chunk])
+        assert np.array_equal(net_in, eng.input_view[: chunk.stop - chunk.start].cpu().numpy())
+        assert np.array_equal(fc, vc) and np.array_equal(fb, vb)
 
 
 def test_cycle_predict_all_matches_oracle():

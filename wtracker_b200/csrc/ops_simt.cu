@@ -337,21 +337,22 @@ constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16x2 (-inf, -inf)
 
 template <bool kToGlobal>
 __device__ __forceinline__ void pool_slide(const uint4* in, uint4* out, int len, int pitch, __nv_bfloat16* gdst,
-                                           size_t gpitch) {
+                                           size_t gpitch, int s0, int s1) {
     const uint4 neg = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
-    uint4 v0 = in[0];
-    uint4 vp1 = len > 1 ? in[pitch] : neg;
-    uint4 pm2 = neg, pm1 = v0;                  // p[x - 2], p[x - 1] at x = 0 (p[-1] = max(-inf, v[0]))
-    uint4 p0 = max_bf16x8(v0, vp1);             // p[x]
-    for (int x0 = 0; x0 < len; x0 += 4) {
+    auto ld = [&](int x) { return (x >= 0 && x < len) ? in[x * pitch] : neg; };
+    const uint4 vm1 = ld(s0 - 1);
+    uint4 v0 = ld(s0), vp1 = ld(s0 + 1);
+    uint4 pm2 = max_bf16x8(ld(s0 - 2), vm1), pm1 = max_bf16x8(vm1, v0);   // p[x - 2], p[x - 1]
+    uint4 p0 = max_bf16x8(v0, vp1);                                          // p[x]
+    for (int x0 = s0; x0 < s1; x0 += 4) {
         uint4 nx[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) nx[k] = x0 + k + 2 < len ? in[(x0 + k + 2) * pitch] : neg;   // v[x + 2]
+        for (int k = 0; k < 4; ++k) nx[k] = ld(x0 + k + 2);                  // v[x + 2]
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int x = x0 + k;
-            if (x < len) {
-                const uint4 p1 = max_bf16x8(vp1, nx[k]);                  // p[x + 1]
+            if (x < s1) {
+                const uint4 p1 = max_bf16x8(vp1, nx[k]);                     // p[x + 1]
                 const uint4 m = max_bf16x8(max_bf16x8(pm2, v0), p1);
                 out[x * pitch] = m;
                 if (kToGlobal) *reinterpret_cast<uint4*>(gdst + size_t(x) * gpitch) = m;
@@ -362,9 +363,11 @@ __device__ __forceinline__ void pool_slide(const uint4* in, uint4* out, int len,
     }
 }
 
+// 256 threads = 64 (line, segment) units x 4 channel groups: a row (column) is walked in `segs` pieces by different
+// threads (each starts its window two pixels early), so 60 of the 64 units work on a 20 x 20 map.
 __global__ void __launch_bounds__(256) sppf_pool_slide_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
                                                               __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c,
-                                                              int h, int w) {
+                                                              int h, int w, int segs) {
     extern __shared__ uint4 pool_smem[];
     constexpr int G = 4;
     const int pw = w + 1, hw = h * w;
@@ -373,10 +376,11 @@ __global__ void __launch_bounds__(256) sppf_pool_slide_kernel(const __nv_bfloat1
     const int n = blockIdx.y;
     const int g = threadIdx.x & (G - 1), u = threadIdx.x >> 2, units = blockDim.x >> 2;
     const int c0 = (blockIdx.x * G + g) * kPoolCg;
+    const int line = u / segs, seg = u - line * segs;
+    const int wseg = (w + segs - 1) / segs, hseg = (h + segs - 1) / segs;
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
-    // every thread of the CTA loads (the sliding passes below occupy only max(h, w) x 4 of them): independent loads,
-    // four in flight per thread
+    // every thread of the CTA loads: independent loads, four in flight per thread
 #pragma unroll 4
     for (int i = u; i < hw; i += units) {
         const int y = i / w;
@@ -384,11 +388,14 @@ __global__ void __launch_bounds__(256) sppf_pool_slide_kernel(const __nv_bfloat1
     }
     __syncthreads();
     for (int round = 0; round < 3; ++round) {
-        if (u < h) pool_slide<false>(cur + u * pw * G + g, tmp + u * pw * G + g, w, G, nullptr, 0);
+        if (line < h)
+            pool_slide<false>(cur + line * pw * G + g, tmp + line * pw * G + g, w, G, nullptr, 0, seg * wseg,
+                              min(w, (seg + 1) * wseg));
         __syncthreads();
-        if (u < w)
-            pool_slide<true>(tmp + u * G + g, cur + u * G + g, h, pw * G,
-                             dst + (size_t(n) * hw + u) * dct + dcoff + round * c + c0, size_t(w) * dct);
+        if (line < w)
+            pool_slide<true>(tmp + line * G + g, cur + line * G + g, h, pw * G,
+                             dst + (size_t(n) * hw + line) * dct + dcoff + round * c + c0, size_t(w) * dct, seg * hseg,
+                             min(h, (seg + 1) * hseg));
         __syncthreads();
     }
 }
@@ -489,7 +496,8 @@ int sppf_pool_launch(const TensorView& src, const TensorView& dst, int c, int n_
         WT_CHECK_CUDA(opt_in_smem(sppf_pool_slide_kernel, opt_in, smem));
         WT_CHECK_CUDA(launch_pdl(sppf_pool_slide_kernel, dim3(c / (kPoolCg * 4), n_images), dim3(256), smem,
                                  stream, static_cast<const __nv_bfloat16*>(src.base), src.ctot, src.coff,
-                                 static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w));
+                                 static_cast<__nv_bfloat16*>(dst.base), dst.ctot, dst.coff, c, src.h, src.w,
+                                 64 / (src.h > src.w ? src.h : src.w)));
         WT_LAUNCHED();
         return 0;
     }

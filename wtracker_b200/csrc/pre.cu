@@ -291,11 +291,13 @@ __global__ void __launch_bounds__(256) pre_resize_kernel(const PreParams p, int 
     // the taps of this thread's first column group: table loads in flight while the rows are staged
     const int groups = lb.dst_w >> 2;
     ResizeTaps t = resize_taps(lb, min(int(threadIdx.x), groups - 1) << 2);
-    // the whole staged row (pitch bytes + one word of slack) lies inside the frame row: word loads
-    const bool x_in = cx >= 0 && cx + pitch + 4 <= p.fw;
+    // word loads where the view's columns lie inside the frame row and the staged span (pitch bytes + one word of slack,
+    // which may run into the next row: those bytes are never used) ends inside the `frames` allocation
+    const bool x_in = cx >= 0 && cx + lb.src_w <= p.fw;
+    const uint8_t* frames_end = p.frames + size_t(p.n_frames) * p.fh * p.fw;
     for (int r = warp; r < nrows; r += warps) {
         const uint8_t* srow = frame + size_t(clampi(cy + vbase + r, 0, p.fh - 1)) * p.fw;
-        if (x_in) {
+        if (x_in && srow + cx + pitch + 4 <= frames_end) {
             const uint8_t* src = srow + cx;
             const uint32_t m = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
             const uint32_t* base = reinterpret_cast<const uint32_t*>(src - m);

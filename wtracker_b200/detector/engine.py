@@ -160,6 +160,39 @@ class DetectorEngine:
         mark()
         return self.out_boxes[:n], self.out_count[:n]
 
+    # CUDA graph of the three stages for small host batches (the per-cycle calls of the simulator: 1, 9 or 15 views).
+    # Such a call is launch-bound — ~59 launches of a few microseconds each — so the stages are captured once per
+    # (batch, source buffer) on the engine's static buffers and replayed; the programmatic-dependent-launch edges and the
+    # fork / join of the engine's side stream are part of the capture.  ``graph_max_batch = 0`` switches it off.
+    graph_max_batch = 16
+
+    def _detect_crops_graphed(self, frames: torch.Tensor, frame_idx: torch.Tensor, crop_x: torch.Tensor, crop_y: torch.Tensor):
+        n = int(frame_idx.numel())
+        if n > self.graph_max_batch:
+            return self.detect_crops(frames, frame_idx, crop_x, crop_y)
+        key = (n, frames.data_ptr(), frame_idx.data_ptr(), crop_x.data_ptr(), crop_y.data_ptr(), self.out_boxes.data_ptr())
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is None:                                # first call with these buffers: run eagerly (warms every kernel up) ...
+            graphs[key] = False
+            return self.detect_crops(frames, frame_idx, crop_x, crop_y)
+        if g is False:                               # ... second call: capture
+            torch.cuda.current_stream().synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.detect_crops(frames, frame_idx, crop_x, crop_y)
+                graphs[key] = g
+            except Exception as e:                   # same kernels, launched one by one
+                import warnings
+
+                warnings.warn(f"DetectorEngine: CUDA graph capture failed ({e}); small batches are launched eagerly")
+                self.graph_max_batch = 0
+                torch.cuda.synchronize()
+                return self.detect_crops(frames, frame_idx, crop_x, crop_y)
+        g.replay()
+        return self.out_boxes[:n], self.out_count[:n]
+
     def _host_staging(self):
         """Persistent staging of the host path (allocated once): pinned view buffer, device view buffer, index
         vectors and a pinned mirror of the packed result words."""
@@ -177,9 +210,54 @@ class DetectorEngine:
     def detect_frames(self, frames: list[np.ndarray], crop_x: list[int], crop_y: list[int]) -> tuple[np.ndarray, np.ndarray]:
         """Host path with the crop on the device (frame ingest: reference utils/frame_reader.py:137-144 +
         view_controller.py:45-61): ``frames`` are whole (H, W) u8 grey frames, ``crop_x / crop_y`` the camera-view
-        origins in frame coordinates (may hang over the border: replicate).  The frames go through a persistent pinned
-        buffer to the device in ONE copy per chunk, the crop kernel cuts the views there.  Same return as
-        ``detect_views``."""
+        origins in frame coordinates (may hang over the border: replicate).  Same return as ``detect_views``.
+
+        A frame is used for ONE view here, so only the view-sized WINDOW of the frame that contains the view's pixels
+        travels: the window is the view rectangle shifted to lie inside the frame (a strided copy straight from the frame
+        into the persistent pinned buffer, one H2D per chunk), and the crop kernel cuts the view out of it at the
+        origin (x0 - window x, y0 - window y) — non-zero exactly where the view hangs over the border, where the kernel's
+        clamp-addressing replicates the window's edge = the frame's edge.  16x fewer bytes than the whole frame at the
+        reference's 360-pixel view.  Views larger than the frame take the whole-frame route (`_detect_whole_frames`)."""
+        n = len(frames)
+        fh, fw = frames[0].shape
+        h, w = self.lb.src_h, self.lb.src_w
+        if h > fh or w > fw:
+            return self._detect_whole_frames(frames, crop_x, crop_y)
+        boxes = np.zeros((n, self.max_det, 6), np.float32)
+        counts = np.zeros((n,), np.int32)
+        with torch.cuda.device(self.device):
+            self._host_staging()
+            if not hasattr(self, "_h_desc"):
+                self._h_desc = torch.zeros((2, self.batch), dtype=torch.int32).pin_memory()
+                self._d_desc = torch.zeros((2, self.batch), dtype=torch.int32, device=self.device)
+            stream = torch.cuda.current_stream()
+            own = self.out_boxes.data_ptr() == self._out_words.data_ptr()
+            hd = self._h_desc.numpy()
+            for s in range(0, n, self.batch):
+                m = min(self.batch, n - s)
+                for i in range(m):
+                    f = frames[s + i]
+                    assert f.shape == (fh, fw) and f.dtype == np.uint8, "frames must be grey u8 of one size"
+                    x0, y0 = int(crop_x[s + i]), int(crop_y[s + i])
+                    wx, wy = min(max(x0, 0), fw - w), min(max(y0, 0), fh - h)
+                    np.copyto(self._h_views_np[i], f[wy: wy + h, wx: wx + w])
+                    hd[0, i], hd[1, i] = x0 - wx, y0 - wy
+                self._d_views[:m].copy_(self._h_views[:m], non_blocking=True)
+                self._d_desc.copy_(self._h_desc, non_blocking=True)
+                b, c = self._detect_crops_graphed(self._d_views, self._iota[:m], self._d_desc[0, :m], self._d_desc[1, :m])
+                if own:
+                    self._h_out.copy_(self._out_words, non_blocking=True)
+                    stream.synchronize()
+                    boxes[s: s + m] = self._h_boxes[:m]
+                    counts[s: s + m] = self._h_count[:m]
+                else:
+                    boxes[s: s + m] = b.cpu().numpy()
+                    counts[s: s + m] = c.cpu().numpy()
+        return boxes, counts
+
+    def _detect_whole_frames(self, frames: list[np.ndarray], crop_x: list[int], crop_y: list[int]) -> tuple[np.ndarray, np.ndarray]:
+        """``detect_frames`` with the whole frames on the device (views larger than the frame; also what
+        ``HotPath.run_frames`` does for streams of frames that are cropped more than once)."""
         n = len(frames)
         fh, fw = frames[0].shape
         boxes = np.zeros((n, self.max_det, 6), np.float32)
@@ -191,21 +269,21 @@ class DetectorEngine:
                 self._h_frames = torch.empty((self.batch, fh, fw), dtype=torch.uint8).pin_memory()
                 self._h_frames_np = self._h_frames.numpy()
                 self._d_frames = torch.empty((self.batch, fh, fw), dtype=torch.uint8, device=self.device)
-                self._h_desc = torch.zeros((2, self.batch), dtype=torch.int32).pin_memory()
-                self._d_desc = torch.zeros((2, self.batch), dtype=torch.int32, device=self.device)
+                self._h_fdesc = torch.zeros((2, self.batch), dtype=torch.int32).pin_memory()
+                self._d_fdesc = torch.zeros((2, self.batch), dtype=torch.int32, device=self.device)
             stream = torch.cuda.current_stream()
             own = self.out_boxes.data_ptr() == self._out_words.data_ptr()
             for s in range(0, n, self.batch):
                 m = min(self.batch, n - s)
-                hd = self._h_desc.numpy()
+                hd = self._h_fdesc.numpy()
                 for i in range(m):
                     f = frames[s + i]
                     assert f.shape == (fh, fw) and f.dtype == np.uint8, "frames must be grey u8 of one size"
                     np.copyto(self._h_frames_np[i], f)
                     hd[0, i], hd[1, i] = crop_x[s + i], crop_y[s + i]
                 self._d_frames[:m].copy_(self._h_frames[:m], non_blocking=True)
-                self._d_desc.copy_(self._h_desc, non_blocking=True)
-                b, c = self.detect_crops(self._d_frames, self._iota[:m], self._d_desc[0, :m], self._d_desc[1, :m])
+                self._d_fdesc.copy_(self._h_fdesc, non_blocking=True)
+                b, c = self._detect_crops_graphed(self._d_frames, self._iota[:m], self._d_fdesc[0, :m], self._d_fdesc[1, :m])
                 if own:
                     self._h_out.copy_(self._out_words, non_blocking=True)
                     stream.synchronize()
@@ -236,7 +314,7 @@ class DetectorEngine:
                     assert v.shape == (h, w), f"views must be {(h, w)}, got {tuple(v.shape)}"
                     np.copyto(self._h_views_np[i], v)
                 self._d_views[:m].copy_(self._h_views[:m], non_blocking=True)
-                b, c = self.detect_crops(self._d_views, self._iota[:m], self._zeros[:m], self._zeros[:m])
+                b, c = self._detect_crops_graphed(self._d_views, self._iota[:m], self._zeros[:m], self._zeros[:m])
                 if own:
                     self._h_out.copy_(self._out_words, non_blocking=True)
                     stream.synchronize()
