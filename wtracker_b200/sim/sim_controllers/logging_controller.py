@@ -169,8 +169,13 @@ class LoggingController(SimController):
         self.log_config.create_dirs()
         self._image_saver = _Saver()
         self._image_saver.start()
-        self._frame_saver = _Saver(deepcopy(sim.view._frame_reader))
-        self._frame_saver.start()
+        # (the reference copies the reader for its FrameSaver unconditionally; an in-memory reader is hundreds of MB, and
+        # the copy is only ever read when worm views are saved)
+        self._frame_saver = None
+        if self.log_config.save_wrm_view:
+            self._frame_saver = _Saver(deepcopy(sim.view._frame_reader))
+            self._frame_saver.start()
+        self._stage = None
         self._bbox_logger = CSVLogger(self.log_config.bbox_file_path, col_names=list(LOG_COLUMNS))
 
     def on_cycle_start(self, sim: Simulator):
@@ -188,20 +193,52 @@ class LoggingController(SimController):
         if self.log_config.save_mic_view:
             self._image_saver.schedule_save(sim.view.micro_view(), self.log_config.mic_file_path.format(sim.frame_number))
 
+    def _staging(self, n: int):
+        """Persistent buffers of the per-cycle log call: ONE pinned input block (worm boxes | camera | microscope boxes |
+        platform positions) with its device mirror, ONE device output block (table | crop | legal) with its pinned
+        mirror — a cycle is one H2D, one kernel, one D2H and one stream synchronize, nothing allocated."""
+        if self._stage is None or self._stage["n"] != n:
+            dev = torch.device(self.device)
+            in_bytes, out_bytes = 72 * n, 160 * n              # 32 + 16 + 16 + 8 ; 136 + 16 + 8
+            h_in = torch.zeros(in_bytes, dtype=torch.uint8).pin_memory()
+            h_out = torch.zeros(out_bytes, dtype=torch.uint8).pin_memory()
+            d_in = torch.zeros(in_bytes, dtype=torch.uint8, device=dev)
+            d_out = torch.zeros(out_bytes, dtype=torch.uint8, device=dev)
+            hn, on = h_in.numpy(), h_out.numpy()
+            self._stage = dict(
+                n=n, h_in=h_in, h_out=h_out, d_in=d_in, d_out=d_out,
+                worm64=hn[: 32 * n].view(np.float64).reshape(n, 4), worm32=hn[: 16 * n].view(np.float32).reshape(n, 4),
+                cam=hn[32 * n: 48 * n].view(np.int32).reshape(n, 4), mic=hn[48 * n: 64 * n].view(np.int32).reshape(n, 4),
+                plt=hn[64 * n: 72 * n].view(np.int32).reshape(n, 2),
+                table=on[: 136 * n].view(np.float64).reshape(n, 17), crop=on[136 * n: 152 * n].view(np.int32).reshape(n, 4),
+                legal=on[152 * n: 153 * n])
+        return self._stage
+
     def _log_cycle(self, sim: Simulator):
         cycle_number = sim.cycle_number - 1
         n_cyc = self.timing_config.cycle_frame_num
         frame_offset = cycle_number * n_cyc
         worm = np.asarray(self.sim_controller._cycle_predict_all(sim))
         dtype = worm.dtype if worm.dtype in (np.float32, np.float64) else np.dtype(np.float64)
-        dev = torch.device(self.device)
-        table, crop, legal = log_table_device(
-            torch.from_numpy(np.ascontiguousarray(worm, dtype=dtype)).to(dev),
-            torch.tensor(np.asarray(list(self._camera_bboxes)), dtype=torch.int32),
-            torch.tensor(np.asarray(list(self._micro_bboxes)), dtype=torch.int32),
-            torch.tensor(np.asarray(list(self._platform_positions)), dtype=torch.int32),
-            frame_offset, n_cyc, self.timing_config.imaging_frame_num, sim.experiment_config.orig_resolution)
-        table, crop, legal = table.cpu().numpy(), crop.cpu().numpy(), legal.cpu().numpy().astype(bool)
+        n = worm.shape[0]
+        assert len(self._camera_bboxes) == len(self._micro_bboxes) == len(self._platform_positions) == n
+        st = self._staging(n)
+        (st["worm32"] if dtype == np.float32 else st["worm64"])[...] = worm
+        st["cam"][...] = self._camera_bboxes
+        st["mic"][...] = self._micro_bboxes
+        st["plt"][...] = self._platform_positions
+        with torch.cuda.device(torch.device(self.device)):
+            stream = torch.cuda.current_stream()
+            st["d_in"].copy_(st["h_in"], non_blocking=True)
+            i0, o0 = st["d_in"].data_ptr(), st["d_out"].data_ptr()
+            bounds = sim.experiment_config.orig_resolution
+            L.check(L.lib().wt_log_rows(i0, int(dtype == np.float32), i0 + 32 * n, i0 + 48 * n, i0 + 64 * n, n,
+                                        int(frame_offset), int(n_cyc), int(self.timing_config.imaging_frame_num),
+                                        int(bounds[0]), int(bounds[1]), o0, o0 + 136 * n, o0 + 152 * n, stream.cuda_stream),
+                    "wt_log_rows")
+            st["h_out"].copy_(st["d_out"], non_blocking=True)
+            stream.synchronize()
+        table, crop, legal = st["table"], st["crop"], st["legal"].astype(bool)
         if self.log_config.save_wrm_view:
             for i in np.nonzero(legal)[0]:
                 frame_number = frame_offset + int(i)
@@ -222,7 +259,8 @@ class LoggingController(SimController):
     def on_sim_end(self, sim: Simulator):
         self.sim_controller.on_sim_end(sim)
         self._image_saver.close()
-        self._frame_saver.close()
+        if self._frame_saver is not None:
+            self._frame_saver.close()
         self._bbox_logger.close()
 
     def on_imaging_start(self, sim: Simulator):
