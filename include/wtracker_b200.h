@@ -276,7 +276,8 @@ int wt_mse_error(const double* worm_xywh, const double* mic_xywh, double* err, i
  *               mic_x, mic_y, mic_w, mic_h, wrm_x, wrm_y, wrm_w, wrm_h   (the csv column order; wrm absolute,
  *               rows without a prediction are 0, 0, 0, 0 exactly as the reference logs them)
  *   crop_xywh : i32 [n][4] integer crop of the worm view clipped to the frame (0 if empty), crop_legal: u8 [n]
- * cycle = frame / cycle_frame_num, phase = (frame % cycle_frame_num) < imaging_frame_num.                          */
+ * cycle = frame / cycle_frame_num, phase = (frame % cycle_frame_num) < imaging_frame_num.
+ * worm_rel, cam_xywh, mic_xywh, crop_xywh: 16-byte aligned (rows move as 128-bit words); plt_xy, table: 8-byte aligned. */
 int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t* cam_xywh, const int32_t* mic_xywh,
                 const int32_t* plt_xy, int64_t n, int64_t first_frame, int cycle_frame_num, int imaging_frame_num,
                 int frame_h, int frame_w, double* table, int32_t* crop_xywh, uint8_t* crop_legal, void* stream);

@@ -89,6 +89,10 @@ extern "C" int wt_log_rows(const void* worm_rel, int worm_is_f32, const int32_t*
     if (n == 0) return 0;
     WT_REQUIRE(worm_rel && cam_xywh && mic_xywh && plt_xy && table && crop_xywh && crop_legal, "null argument");
     WT_REQUIRE(cycle_frame_num >= 1 && imaging_frame_num >= 0 && first_frame >= 0, "cycle geometry");
+    auto aligned16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+    WT_REQUIRE(aligned16(worm_rel) && aligned16(cam_xywh) && aligned16(mic_xywh) && aligned16(crop_xywh) &&
+                   reinterpret_cast<uintptr_t>(plt_xy) % 8 == 0 && reinterpret_cast<uintptr_t>(table) % 8 == 0,
+               "wt_log_rows: box arrays must be 16-byte aligned (rows are read / written as 128-bit words)");
     LogParams p;
     p.worm_rel = worm_rel;
     p.worm_is_f32 = worm_is_f32;

@@ -166,12 +166,15 @@ __global__ void __launch_bounds__(256) pre_crop_kernel(const PreParams p) {
     const int X0 = (gid - Yq * groups_per_row) << 4;
     const uint8_t* frame = p.frames + size_t(clampi(p.frame_idx[img], 0, p.n_frames - 1)) * p.fh * p.fw;
     const int cx = p.crop_x[img], cy = p.crop_y[img];
-    const bool x_in = cx + X0 >= 0 && cx + X0 + 32 <= p.fw;   // one group of slack for the second vector load
+    // the 16 pixels lie inside the frame row; the second vector load may run up to 16 bytes past them — into the next
+    // row (bytes shifted out) — so it only has to end inside the `frames` allocation (tight windows: fw == view width)
+    const bool x_in = cx + X0 >= 0 && cx + X0 + 16 <= p.fw;
+    const uint8_t* frames_end = p.frames + size_t(p.n_frames) * p.fh * p.fw;
     uint4 v[kCropRows];
 #pragma unroll
     for (int r = 0; r < kCropRows; ++r) {
         const uint8_t* srow = frame + size_t(clampi(cy + Yq * kCropRows + r, 0, p.fh - 1)) * p.fw;
-        if (x_in) {
+        if (x_in && srow + cx + X0 + 32 <= frames_end) {
             v[r] = load16_unaligned(srow + cx + X0);
         } else {   // the view hangs over the left / right frame border: replicate per byte
             uint32_t w[4] = {0u, 0u, 0u, 0u};

@@ -199,19 +199,28 @@ class LoggingController(SimController):
         mirror — a cycle is one H2D, one kernel, one D2H and one stream synchronize, nothing allocated."""
         if self._stage is None or self._stage["n"] != n:
             dev = torch.device(self.device)
-            in_bytes, out_bytes = 72 * n, 160 * n              # 32 + 16 + 16 + 8 ; 136 + 16 + 8
+            al = lambda v: (v + 255) & ~255                    # every block 256-byte aligned (the kernel uses 16-byte accesses)
+            o_cam = al(32 * n)
+            o_mic = o_cam + al(16 * n)
+            o_plt = o_mic + al(16 * n)
+            in_bytes = o_plt + al(8 * n)
+            o_crop = al(136 * n)
+            o_legal = o_crop + al(16 * n)
+            out_bytes = o_legal + al(n)
             h_in = torch.zeros(in_bytes, dtype=torch.uint8).pin_memory()
             h_out = torch.zeros(out_bytes, dtype=torch.uint8).pin_memory()
             d_in = torch.zeros(in_bytes, dtype=torch.uint8, device=dev)
             d_out = torch.zeros(out_bytes, dtype=torch.uint8, device=dev)
             hn, on = h_in.numpy(), h_out.numpy()
             self._stage = dict(
-                n=n, h_in=h_in, h_out=h_out, d_in=d_in, d_out=d_out,
+                n=n, h_in=h_in, h_out=h_out, d_in=d_in, d_out=d_out, o_cam=o_cam, o_mic=o_mic, o_plt=o_plt, o_crop=o_crop,
+                o_legal=o_legal,
                 worm64=hn[: 32 * n].view(np.float64).reshape(n, 4), worm32=hn[: 16 * n].view(np.float32).reshape(n, 4),
-                cam=hn[32 * n: 48 * n].view(np.int32).reshape(n, 4), mic=hn[48 * n: 64 * n].view(np.int32).reshape(n, 4),
-                plt=hn[64 * n: 72 * n].view(np.int32).reshape(n, 2),
-                table=on[: 136 * n].view(np.float64).reshape(n, 17), crop=on[136 * n: 152 * n].view(np.int32).reshape(n, 4),
-                legal=on[152 * n: 153 * n])
+                cam=hn[o_cam: o_cam + 16 * n].view(np.int32).reshape(n, 4),
+                mic=hn[o_mic: o_mic + 16 * n].view(np.int32).reshape(n, 4),
+                plt=hn[o_plt: o_plt + 8 * n].view(np.int32).reshape(n, 2),
+                table=on[: 136 * n].view(np.float64).reshape(n, 17),
+                crop=on[o_crop: o_crop + 16 * n].view(np.int32).reshape(n, 4), legal=on[o_legal: o_legal + n])
         return self._stage
 
     def _log_cycle(self, sim: Simulator):
@@ -232,9 +241,10 @@ class LoggingController(SimController):
             st["d_in"].copy_(st["h_in"], non_blocking=True)
             i0, o0 = st["d_in"].data_ptr(), st["d_out"].data_ptr()
             bounds = sim.experiment_config.orig_resolution
-            L.check(L.lib().wt_log_rows(i0, int(dtype == np.float32), i0 + 32 * n, i0 + 48 * n, i0 + 64 * n, n,
+            L.check(L.lib().wt_log_rows(i0, int(dtype == np.float32), i0 + st["o_cam"], i0 + st["o_mic"], i0 + st["o_plt"], n,
                                         int(frame_offset), int(n_cyc), int(self.timing_config.imaging_frame_num),
-                                        int(bounds[0]), int(bounds[1]), o0, o0 + 136 * n, o0 + 152 * n, stream.cuda_stream),
+                                        int(bounds[0]), int(bounds[1]), o0, o0 + st["o_crop"], o0 + st["o_legal"],
+                                        stream.cuda_stream),
                     "wt_log_rows")
             st["h_out"].copy_(st["d_out"], non_blocking=True)
             stream.synchronize()
