@@ -335,29 +335,32 @@ __global__ void __launch_bounds__(kPoolThreads * G) sppf_pool_kernel(const __nv_
 // the two rows (columns) of a quarter-warp fall into different halves of the 32 banks.
 constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16x2 (-inf, -inf)
 
+// Outputs [s0, s1) of one line (row or column) of length `len`: chunks of kPoolChunk outputs whose kPoolChunk + 4 inputs
+// sit in registers with static indices (no window rotation: ncu showed the rotating form spending most of its issue slots
+// on register moves and per-step bounds checks).
+constexpr int kPoolChunk = 7;
+
 template <bool kToGlobal>
 __device__ __forceinline__ void pool_slide(const uint4* in, uint4* out, int len, int pitch, __nv_bfloat16* gdst,
                                            size_t gpitch, int s0, int s1) {
     const uint4 neg = make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
-    auto ld = [&](int x) { return (x >= 0 && x < len) ? in[x * pitch] : neg; };
-    const uint4 vm1 = ld(s0 - 1);
-    uint4 v0 = ld(s0), vp1 = ld(s0 + 1);
-    uint4 pm2 = max_bf16x8(ld(s0 - 2), vm1), pm1 = max_bf16x8(vm1, v0);   // p[x - 2], p[x - 1]
-    uint4 p0 = max_bf16x8(v0, vp1);                                          // p[x]
-    for (int x0 = s0; x0 < s1; x0 += 4) {
-        uint4 nx[4];
+    for (int c = s0; c < s1; c += kPoolChunk) {
+        uint4 v[kPoolChunk + 4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) nx[k] = ld(x0 + k + 2);                  // v[x + 2]
+        for (int i = 0; i < kPoolChunk + 4; ++i) {
+            const int x = c - 2 + i;
+            v[i] = (x >= 0 && x < len && x < s1 + 2) ? in[x * pitch] : neg;
+        }
+        uint4 pr[kPoolChunk + 3];                                       // pr[i] = max(v[i], v[i + 1])
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = x0 + k;
+        for (int i = 0; i < kPoolChunk + 3; ++i) pr[i] = max_bf16x8(v[i], v[i + 1]);
+#pragma unroll
+        for (int o = 0; o < kPoolChunk; ++o) {
+            const int x = c + o;
             if (x < s1) {
-                const uint4 p1 = max_bf16x8(vp1, nx[k]);                     // p[x + 1]
-                const uint4 m = max_bf16x8(max_bf16x8(pm2, v0), p1);
+                const uint4 m = max_bf16x8(max_bf16x8(pr[o], v[o + 2]), pr[o + 3]);
                 out[x * pitch] = m;
                 if (kToGlobal) *reinterpret_cast<uint4*>(gdst + size_t(x) * gpitch) = m;
-                pm2 = pm1; pm1 = p0; p0 = p1;
-                v0 = vp1; vp1 = nx[k];
             }
         }
     }
@@ -365,7 +368,7 @@ __device__ __forceinline__ void pool_slide(const uint4* in, uint4* out, int len,
 
 // 256 threads = 64 (line, segment) units x 4 channel groups: a row (column) is walked in `segs` pieces by different
 // threads (each starts its window two pixels early), so 60 of the 64 units work on a 20 x 20 map.
-__global__ void __launch_bounds__(256) sppf_pool_slide_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
+__global__ void __launch_bounds__(256, 4) sppf_pool_slide_kernel(const __nv_bfloat16* __restrict__ src, int sct, int scoff,
                                                               __nv_bfloat16* __restrict__ dst, int dct, int dcoff, int c,
                                                               int h, int w, int segs) {
     extern __shared__ uint4 pool_smem[];
