@@ -7,7 +7,7 @@ some buffers are reused later in the pass.
 Tolerance per op (printed, and written to gpurun_out/layer_parity.json): the kernel accumulates in fp32 from the same bf16
 operands; what differs is the accumulation order, tanh.approx in SiLU and the final rounding to bf16 (2^-9 relative), so
 mean |err| <= 0.3 % of the reference's standard deviation and max |err| <= 1.5 % of its largest magnitude (measured
-worst over the 54 ops at both network sizes: 0.105 % and 0.53 %, the chained layer 1).  A wrong tap, a swapped channel
+worst over the 54 ops at both network sizes: 0.126 % and 0.53 %).  A wrong tap, a swapped channel
 block or a missing residual gives errors of order 100 %."""
 import json
 import os
