@@ -165,3 +165,27 @@ def test_file_reader_listing_stream_and_batches(tmp_path):
     assert np.array_equal(a.read_batch(range(1, 4)), np.stack(imgs[1:4])) and a.frame_shape == (24, 32)
     d = DummyReader(3, (10, 12), colored=False)
     assert len(d) == 3 and d.frame_shape == (10, 12) and (d[1] == 255).all()
+
+
+def test_ingest_window_plus_clamped_crop_equals_camera_view():
+    """Frame ingest (DetectorEngine.detect_frames): a view-sized window of the frame travels to the GPU and the crop kernel
+    cuts the view out of it with clamp-addressing.  Host statement of that kernel here: for origins inside the frame, over
+    every border, over corners and entirely outside, window + clamped crop must give exactly the replicate-border view the
+    reference buffers (view_controller.py:45-61,158-172)."""
+    from wtracker_b200 import synth
+    from wtracker_b200.detector.engine import ingest_window
+
+    rng = np.random.default_rng(0)
+    fh, fw = 108, 192
+    frame = rng.integers(0, 256, (fh, fw), dtype=np.uint8)
+    for size in (36, 64, 108):
+        origins = [(10, 20), (-7, 30), (fw - 20, 5), (40, -9), (60, fh - 11), (-15, -15), (fw - 3, fh - 2), (-500, 40),
+                   (fw + 300, fh + 300), (0, 0), (fw - size, fh - size)]
+        for x0, y0 in origins:
+            wx, wy, cx, cy = ingest_window(x0, y0, size, size, fw, fh)
+            assert 0 <= wx <= fw - size and 0 <= wy <= fh - size
+            window = frame[wy: wy + size, wx: wx + size]
+            ys = np.clip(cy + np.arange(size), 0, size - 1)          # the crop kernel's addressing inside the window
+            xs = np.clip(cx + np.arange(size), 0, size - 1)
+            want = synth.camera_view(frame, (x0 + size // 2, y0 + size // 2), size)
+            assert np.array_equal(window[np.ix_(ys, xs)], want), (size, x0, y0)

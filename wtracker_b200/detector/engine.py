@@ -28,6 +28,16 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def ingest_window(x0: int, y0: int, w: int, h: int, fw: int, fh: int) -> tuple[int, int, int, int]:
+    """Frame ingest of one view (``DetectorEngine.detect_frames``): the (w, h) window of an (fw, fh) frame that travels to the
+    GPU for the camera view with origin (x0, y0) — the view rectangle shifted to lie inside the frame — and the crop origin
+    (cx, cy) inside that window.  The crop kernel clamps its addresses to the window, which replicates the window's edge
+    where the view hangs over the frame border: exactly the frame's edge, because the window touches that border."""
+    assert w <= fw and h <= fh
+    wx, wy = min(max(x0, 0), fw - w), min(max(y0, 0), fh - h)
+    return wx, wy, x0 - wx, y0 - wy
+
+
 class DetectorEngine:
     """YOLOv8 detector for views of a fixed size ``view_hw`` letterboxed to ``imgsz``.
 
@@ -239,9 +249,8 @@ class DetectorEngine:
                     f = frames[s + i]
                     assert f.shape == (fh, fw) and f.dtype == np.uint8, "frames must be grey u8 of one size"
                     x0, y0 = int(crop_x[s + i]), int(crop_y[s + i])
-                    wx, wy = min(max(x0, 0), fw - w), min(max(y0, 0), fh - h)
+                    wx, wy, hd[0, i], hd[1, i] = ingest_window(x0, y0, w, h, fw, fh)
                     np.copyto(self._h_views_np[i], f[wy: wy + h, wx: wx + w])
-                    hd[0, i], hd[1, i] = x0 - wx, y0 - wy
                 self._d_views[:m].copy_(self._h_views[:m], non_blocking=True)
                 self._d_desc.copy_(self._h_desc, non_blocking=True)
                 b, c = self._detect_crops_graphed(self._d_views, self._iota[:m], self._d_desc[0, :m], self._d_desc[1, :m])
