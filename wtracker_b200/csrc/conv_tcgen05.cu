@@ -97,6 +97,11 @@ struct ConvTcParams {
     // 3x3 layers are bound by the L2 -> shared-memory fill, ~86 % of it weights: DESIGN.md), nt accumulators sit side
     // by side in TMEM and an epilogue group drains all of them.
     int nt;
+    // Split epilogue (plain / residual / addend convs whose work item has >= 2 staging units): BOTH epilogue groups drain
+    // every work item, unit su of item `it` going to group (su + it) & 1, instead of alternating whole items.  Same
+    // epilogue throughput, half the latency per item: the drain after a CTA's last MMA — tensor pipe idle — halves.
+    // tempty / add_empty then collect 16 warp arrivals and accumulator set it & 1 belongs to the item, not to a group.
+    int split;
     // tuning builds: per-CTA event trace (wt_debug_conv_trace): [launch][CTA][4 roles][trace_cap] u64, or nullptr
     unsigned long long* trace;
     int trace_cap;
@@ -314,15 +319,21 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
     const bool rows64 = CW == 16 && !p.out_f32;           // bf16, BN == 32: 64-byte staging rows (SWIZZLE_64B)
     const uint32_t unit_bytes = rows64 ? kTileM * 64 : kTileM * 128;
     uint32_t unit_counter = 0;
-    int it = g;
+    const bool split = p.split != 0;
+    int it = split ? 0 : g;
     const int first = blockIdx.x, step = gridDim.x;
+    const int tile_step = split ? step : 2 * step, it_step = split ? 1 : 2;
     Tracer tr(p, 2 + g, store_thread);
     ptx::grid_dependency_wait();   // residual loads and output stores come after the previous kernel
     tr.ev(1);
-    for (int tile = first + g * step; tile < p.num_tiles; tile += 2 * step, it += 2) {
+    for (int tile = first + (split ? 0 : g * step); tile < p.num_tiles; tile += tile_step, it += it_step) {
         const TileCoord tc = decode_tile(p, tile);
         const int nblk = tc.nblk, x0 = tc.x0, y0 = tc.y0, n0 = tc.n0;
         const uint32_t aphase = (it >> 1) & 1;
+        const int ab = split ? (it & 1) : g;      // accumulator set / addend buffer of this work item
+        // last unit of this work item that this group handles (its TMEM reads and addend reads end there)
+        const int su_last = !split ? NT * kUnits - 1
+                                   : ((((NT * kUnits - 1) + it) & 1) == g ? NT * kUnits - 1 : NT * kUnits - 2);
         const float* bias = sBias + nblk * BN + h * CW;
 
         // Upsampled addend (wt_op.add_buf): warp 2 has TMA-loaded this tile's half-resolution patch into this group's
@@ -333,23 +344,24 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
         if (p.has_add) {
             const int lx = row % p.tw, ly = (row / p.tw) % p.th, ln = row / (p.tw * p.th);
             const int prow = (ln * (p.th >> 1) + (ly >> 1)) * (p.tw >> 1) + (lx >> 1);
-            add_row = sAddAll + g * (BN * 128) + prow * 128;
+            add_row = sAddAll + ab * (BN * 128) + prow * 128;
             add_xr = prow & 7;
-            ptx::mbar_wait(&add_full[g], aphase);
+            ptx::mbar_wait(&add_full[ab], aphase);
         }
 
         tr.ev(19, it);
-        ptx::mbar_wait(&tfull_bar[g], aphase);
+        ptx::mbar_wait(&tfull_bar[ab], aphase);
         ptx::tc_fence_after();
         tr.ev(20, it);
 
 #pragma unroll 1
         for (int su = 0; su < NT * kUnits; ++su) {
+            if (split && ((su + it) & 1) != g) continue;        // the other group's unit
             const int sub = NT == 1 ? 0 : su / kUnits;          // pixel tile of the group (image n0 + sub)
             const int unit = NT == 1 ? su : su - sub * kUnits;
             const int n0s = n0 + sub * p.tn;
             const int cy = p.il == 2 ? n0s : y0, cn = p.il == 2 ? y0 : n0s;   // tensor-map order of the last two coordinates
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * NT + sub) * BN + h * CW;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (ab * NT + sub) * BN + h * CW;
             const int sb = two_bufs ? (unit_counter & 1) : 0;
             uint8_t* stage_buf = sStage + sb * kStageBufBytes;
             uint32_t acc[CW];
@@ -365,12 +377,12 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
                 ptx::tma_load_4d(stage_buf, &p.tmR, &res_bar[sb], p.res_coff + nblk * BN + unit * kUnitCh, x0, cy, cn);
             }
             ptx::tmem_ld_wait();
-            if (su == NT * kUnits - 1) {
+            if (su == su_last) {
                 // all TMEM reads of this warp for this tile are done: hand the accumulator back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::mbar_arrive(&tempty_bar[g]);
+                    ptx::mbar_arrive(&tempty_bar[ab]);
                 }
             }
             float v[CW];
@@ -431,9 +443,9 @@ __device__ __forceinline__ void conv_epilogue_cw(const ConvTcParams& p, uint8_t*
                     for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
                 }
             }
-            if (p.has_add && su == NT * kUnits - 1) {   // this warp is done with the patch: warp 2 may load the group's next one
+            if (p.has_add && su == su_last) {   // this warp is done with the patch: warp 2 may load the next one into it
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&add_empty[g]);
+                if (lane == 0) ptx::mbar_arrive(&add_empty[ab]);
             }
             if (p.has_res) ptx::mbar_wait(&res_bar[sb], (two_bufs ? (unit_counter >> 1) : unit_counter) & 1);
 
@@ -888,12 +900,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 8);   // the 8 warps of an epilogue group
+            ptx::mbar_init(&tempty_bar[i], p.split ? 16 : 8);   // the 8 warps of an epilogue group (split: of both)
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&add_full[i], 1);
-            ptx::mbar_init(&add_empty[i], 8);
+            ptx::mbar_init(&add_empty[i], p.split ? 16 : 8);
         }
         for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
         ptx::mbar_init(w2_full, 1);
@@ -1187,7 +1199,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 8);   // the 8 warps of an epilogue group
+            ptx::mbar_init(&tempty_bar[i], p.split ? 16 : 8);   // the 8 warps of an epilogue group (split: of both)
         }
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < 6; ++i) ptx::mbar_init(&chain_bars[i], i < 4 ? 1 : 8);
@@ -1963,6 +1975,16 @@ int conv_tc_plan_create(const ConvDesc& d, ConvTcPlan** out) {
         pl->smem_bytes = p.stages * stage_bytes + fixed;
     }
 
+    {
+        // split epilogue: both groups drain every work item when it has at least two staging units (units of 64 channels
+        // for bf16 output with BN >= 64, of 32 channels for f32 output; a bf16 BN = 32 tile is one unit)
+        static const int split_env = knob("WT_EPI_SPLIT", 1);
+        const int unit_ch = (bn >= 64 && !out_f32) ? 64 : 32;
+        const int units = p.nt * (bn / unit_ch);
+        // (measured per layer: an odd unit count — BN = 192 — and the addend layers lose with the split, the rest gain)
+        p.split = (split_env && p.chain == 0 && !d.dot_w && units >= 2 && (units % 2 == 0 || split_env == 2) &&
+                   (!d.add.base || split_env == 2)) ? 1 : 0;
+    }
     const int sw_in = bk * 2;   // swizzle span == K-block row bytes
     int rc = 0;
     const uint32_t box_a[4] = {uint32_t(bk), uint32_t(pl->halo ? kHaloW : p.tw), uint32_t(pl->halo ? kHaloH : p.th),
