@@ -2,8 +2,6 @@
 lanes (54 ops) against the same program built without them (57 ops, one stream) on the same input — every tapped
 feature map, the box features and the class logits are compared exactly.  (Per-kernel versions of the same claim:
 wt_selftest_conv_chain / wt_selftest_conv_cat, tools/gpu_conv_selftest.py.)"""
-import os
-
 import pytest
 import torch
 
@@ -13,15 +11,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("view,imgsz", [(360, 384), (640, 640)])
-def test_fused_program_is_bit_identical_to_the_unfused_one(view, imgsz, monkeypatch):
+def test_fused_program_is_bit_identical_to_the_unfused_one(view, imgsz):
     from wtracker_b200 import _lib as L
     from wtracker_b200.detector.engine import DetectorEngine
 
     views = views_for(view, 4)
     fused = DetectorEngine(synthetic_sd(), (view, view), imgsz, batch=4, max_det=1)
-    monkeypatch.setenv("WT_CHAIN", "0")
-    plain = DetectorEngine(synthetic_sd(), (view, view), imgsz, batch=4, max_det=1)
-    monkeypatch.delenv("WT_CHAIN")
+    plain = DetectorEngine(synthetic_sd(), (view, view), imgsz, batch=4, max_det=1, fuse=False)
     assert len(fused.program.ops) == 54 and len(plain.program.ops) == 57
     assert any(o.get("cat_buf", -1) >= 0 for o in fused.program.ops)
     assert sum(1 for o in fused.program.ops if o.get("chain_w_off", -1) >= 0 and o["kind"] == L.WT_OP_CONV) == 3

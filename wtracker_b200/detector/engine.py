@@ -6,7 +6,6 @@ PyTorch is plumbing here (memory + streams); all arithmetic happens in libwtrack
 
 from __future__ import annotations
 
-import os
 
 import ctypes as C
 
@@ -47,7 +46,7 @@ class DetectorEngine:
 
     def __init__(self, state_dict: dict[str, torch.Tensor], view_hw: tuple[int, int], imgsz: int = 384,
                  batch: int = 16, conf: float = 0.1, iou: float = 0.7, max_det: int = 1, device: str = "cuda:0",
-                 conv_impl: int = 0, arch: YoloV8Arch | None = None):
+                 conv_impl: int = 0, arch: YoloV8Arch | None = None, fuse: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("wtracker_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.lib()
@@ -57,7 +56,7 @@ class DetectorEngine:
         self.batch = int(batch)
         self.conf, self.iou, self.max_det = float(conf), float(iou), int(max_det)
         self.program: Program = build_program(state_dict, self.arch, self.lb.dst_h, self.lb.dst_w,
-                                              chain=conv_impl == 0 and os.environ.get("WT_CHAIN", "1") != "0")
+                                              chain=conv_impl == 0 and fuse)   # fuse=False: one launch per conv (tests)
 
         with torch.cuda.device(self.device):
             self.weights = blob_tensor(self.program).to(self.device)

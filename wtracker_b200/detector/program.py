@@ -61,9 +61,8 @@ def build_program(sd: dict[str, torch.Tensor], arch: YoloV8Arch, net_h: int, net
     """``chain``: chain C2f.cv1 onto the stride-2 conv before it where the engine supports it (wt_op.chain_w_off;
     tcgen05 path only, so the scalar validation engine is built with chain=False)."""
     assert net_h % 32 == 0 and net_w % 32 == 0, "network input must be a multiple of 32"
-    if chain_exit is None:        # the C2f-exit concat chain follows `chain` unless switched off (WT_CHAIN_EXIT=0)
-        import os
-        chain_exit = chain and os.environ.get("WT_CHAIN_EXIT", "1") != "0"
+    if chain_exit is None:        # the C2f-exit concat chain follows `chain`
+        chain_exit = chain
     if arch.nc != 1:
         raise NotImplementedError(f"the CUDA detector is built for single-class checkpoints (the reference trains with "
                                   f"single_cls: True, yolo_train_config.yaml:27); this one has nc = {arch.nc}")
