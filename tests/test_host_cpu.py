@@ -189,3 +189,32 @@ def test_ingest_window_plus_clamped_crop_equals_camera_view():
             xs = np.clip(cx + np.arange(size), 0, size - 1)
             want = synth.camera_view(frame, (x0 + size // 2, y0 + size // 2), size)
             assert np.array_equal(window[np.ix_(ys, xs)], want), (size, x0, y0)
+
+
+def test_sine_motor_steps_sum_to_the_requested_move():
+    """Property of the residual-carrying half-cosine profile (motor_controllers.py:70-88) that the lock-step engine's
+    vectorised motor state relies on: whatever the move, the integer steps of one movement phase add up to it exactly
+    (fractions sum to 1 and every rounding error is carried into the next step).  (That the numpy-over-K form of
+    ``BatchedSimulator`` takes the same steps as K scalar controllers is test_batched_cpu.py's subject.)"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from wtracker_b200.sim import ExperimentConfig, TimingConfig
+    from wtracker_b200.sim.motor_controllers import SineMotorController
+
+    def timing(moving_ms):
+        exp = ExperimentConfig("t", 100, 60, (1080, 1920), 90, (960, 540))
+        return TimingConfig(exp, 100, moving_ms, 50, (4.0, 4.0), (0.32, 0.32))
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(-400, 400), st.integers(-400, 400), st.sampled_from([17, 40, 67, 100, 150]))
+    def check(dx, dy, moving_ms):
+        t = timing(moving_ms)
+        m = SineMotorController(t)
+        m.register_move(dx, dy)
+        steps = [m.step() for _ in range(t.moving_frame_num)]
+        assert all(isinstance(v, int) for s in steps for v in s)
+        assert (sum(s[0] for s in steps), sum(s[1] for s in steps)) == (dx, dy)
+        assert len(m.queue) == 0
+
+    check()
